@@ -1,0 +1,377 @@
+// C ABI of the phys-optim path (see include/chd.h).  Host driver: device memory, stage loops, launches.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/chd.h"
+#include "chd_dev.h"
+
+// kernels (chd_kernels.cu)
+__global__ void chd_k_stage_begin(ChdDev D, ChdStageDev sg, int max_iter);
+__global__ void chd_k_eval(ChdDev D, ChdStageDev sg, int only_running);
+__global__ void chd_k_init(ChdDev D);
+__global__ void chd_k_kkt(ChdDev D, ChdStageDev sg);
+__global__ void chd_k_linesearch(ChdDev D, ChdStageDev sg);
+__global__ void chd_k_sample(ChdDev D, double* out, int* frames_out);
+
+#define CHD_CUDA(x)                                                                          \
+  do {                                                                                       \
+    cudaError_t e_ = (x);                                                                    \
+    if (e_ != cudaSuccess) {                                                                 \
+      fprintf(stderr, "libchd: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return -100 - (int)e_;                                                                 \
+    }                                                                                        \
+  } while (0)
+
+enum { KT_EVAL = 0, KT_KKT = 1, KT_LS = 2, KT_INIT = 3, KT_SAMPLE = 4, KT_N = 8 };
+
+struct chd_phys_batch {
+  ChdHostBatch hb;
+  ChdDev D;
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  int timing = 0;
+  bool host_only = false;
+  double kt_ms[KT_N] = {0};
+  int64_t kt_n[KT_N] = {0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int* d_frames = nullptr;
+  double* d_samples = nullptr;
+  size_t smem_eval = 0, smem_kkt = 0, smem_ls = 0;
+  ChdIpm* h_ipm = nullptr;  // pinned
+};
+
+namespace {
+
+template <class T>
+int dev_upload(chd_phys_batch* b, const std::vector<T>& v, const T** out) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  CHD_CUDA(cudaMalloc(&p, bytes));
+  b->allocs.push_back(p);
+  if (!v.empty()) CHD_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = (const T*)p;
+  return 0;
+}
+template <class T>
+int dev_alloc(chd_phys_batch* b, size_t count, T** out) {
+  void* p = nullptr;
+  CHD_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  CHD_CUDA(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+  b->allocs.push_back(p);
+  *out = (T*)p;
+  return 0;
+}
+
+ChdStageDev stage_dev(const ChdStageCfg& c) {
+  ChdStageDev s;
+  s.set_mask = c.set_mask;
+  for (int i = 0; i < 3; ++i) s.w_data[i] = c.w_data[i], s.w_vel[i] = c.w_vel[i], s.w_acc[i] = c.w_acc[i];
+  return s;
+}
+
+struct Timer {
+  chd_phys_batch* b;
+  int id;
+  Timer(chd_phys_batch* bb, int i) : b(bb), id(i) {
+    if (b->timing) cudaEventRecord(b->ev0, b->stream);
+  }
+  ~Timer() {
+    b->launches++;
+    b->kt_n[id]++;
+    if (b->timing) {
+      cudaEventRecord(b->ev1, b->stream);
+      cudaEventSynchronize(b->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+      b->kt_ms[id] += ms;
+    }
+  }
+};
+
+void launch_eval(chd_phys_batch* b, const ChdStageDev& sg, int only_running) {
+  Timer t(b, KT_EVAL);
+  chd_k_eval<<<b->hb.B, CHD_THREADS, b->smem_eval, b->stream>>>(b->D, sg, only_running);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* chd_version(void) { return "libchd 0.1 (sm_100a)"; }
+
+int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const chd_phys_weights* weights, int32_t device,
+                          chd_phys_batch** out) {
+  if (!problems || batch <= 0 || !out) return -1;
+  const bool host_only = device == -2;  // layout tables only, no CUDA call (CPU-side tests of the host logic)
+  if (device >= 0) CHD_CUDA(cudaSetDevice(device));
+  chd_phys_weights w = {0.4, 1.7, 0.3, 0.1, 0.1};  // phys_optim.cpp:27-31
+  if (weights) w = *weights;
+  chd_phys_batch* b = new chd_phys_batch();
+  int rc = chd_build_layout(problems, batch, w, b->hb);
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  ChdHostBatch& hb = b->hb;
+  ChdDev& D = b->D;
+  std::memset(&D, 0, sizeof(D));
+  b->host_only = host_only;
+  if (host_only) {
+    *out = b;
+    return 0;
+  }
+  D.B = hb.B, D.S = hb.S, D.Pmax = hb.Pmax, D.n_max = hb.n_max, D.m_max = hb.m_max, D.slots_max = hb.slots_max;
+  D.sets_max = hb.sets_max, D.tab_max = hb.tab_max, D.F_max = hb.F_max, D.Kd_max = hb.Kd_max, D.Kr_max = hb.Kr_max;
+  D.Na_max = hb.Na_max, D.nb_max = hb.nb_max, D.w_max = hb.w_max, D.par_stride = hb.par_stride(), D.n_ee_max = hb.n_ee_max;
+  D.fo_max = hb.fo_max, D.Ph_max = hb.Ph_max;
+  CHD_CUDA(cudaStreamCreate(&b->stream));
+  CHD_CUDA(cudaEventCreate(&b->ev0));
+  CHD_CUDA(cudaEventCreate(&b->ev1));
+#define UP(field) if ((rc = dev_upload(b, hb.field, &D.field))) return rc;
+  UP(seq) UP(poly_T) UP(poly_tend) UP(node_const) UP(par) UP(t_dyn) UP(t_rom) UP(t_data) UP(row_lo) UP(row_hi) UP(node_var)
+  UP(itab) UP(ent_ptr) UP(ent_col) UP(var_kkt) UP(row_kkt) UP(row_set) UP(sets) UP(phase_tend)
+#undef UP
+  const size_t B = hb.B, nm = B * hb.n_max, mm = B * hb.m_max;
+#define AL(field, cnt) if ((rc = dev_alloc(b, (cnt), &D.field))) return rc;
+  AL(x, nm) AL(xt, nm) AL(dx, nm) AL(grad, nm) AL(g, mm) AL(gt, mm) AL(Jv, B * hb.slots_max) AL(rflag, mm)
+  AL(sc, mm) AL(dL, mm) AL(dU, mm) AL(s, mm) AL(y, mm) AL(zL, mm) AL(zU, mm) AL(ds, mm) AL(dy, mm) AL(dzL, mm) AL(dzU, mm)
+  AL(cost, B * 2) AL(Kband, B * (size_t)hb.Na_max * (hb.w_max + 1)) AL(Kbord, B * (size_t)hb.Na_max * (hb.nb_max + 1))
+  AL(Kcorn, B * (size_t)(hb.nb_max + 1) * (hb.nb_max + 1)) AL(sol, B * (size_t)(hb.Na_max + hb.nb_max)) AL(ipm, B)
+#undef AL
+  CHD_CUDA(cudaMemcpy(D.x, hb.x0.data(), nm * sizeof(double), cudaMemcpyHostToDevice));
+  // shared-memory budgets
+  const size_t W = hb.w_max + 1, nbp = hb.nb_max + 1;
+  b->smem_eval = (2 * (size_t)hb.n_max + CHD_THREADS) * sizeof(double);
+  b->smem_ls = ((size_t)hb.n_max + CHD_THREADS) * sizeof(double);
+  const size_t kkt_fixed = (CHD_THREADS + (size_t)hb.n_max + nbp * nbp + 2 * (W + nbp)) * sizeof(double);
+  const size_t kkt_win = (W * W + W * nbp) * sizeof(double);
+  int dev = 0, smem_max = 0;
+  CHD_CUDA(cudaGetDevice(&dev));
+  CHD_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (kkt_fixed + kkt_win + 1024 <= (size_t)smem_max) {
+    D.win_smem = 1;
+    b->smem_kkt = kkt_fixed + kkt_win;
+  } else {
+    D.win_smem = 0;
+    b->smem_kkt = kkt_fixed;
+    if ((rc = dev_alloc(b, B * (W * W + W * nbp), &D.scratch))) return rc;
+  }
+  if (b->smem_eval + 1024 > (size_t)smem_max || b->smem_kkt + 1024 > (size_t)smem_max) {
+    fprintf(stderr, "libchd: problem too large for the shared-memory staged kernels (n_max=%d)\n", hb.n_max);
+    return -5;
+  }
+  CHD_CUDA(cudaFuncSetAttribute(chd_k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_eval));
+  CHD_CUDA(cudaFuncSetAttribute(chd_k_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_kkt));
+  CHD_CUDA(cudaFuncSetAttribute(chd_k_linesearch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_ls));
+  const size_t stride = 6 + 7 * (size_t)hb.n_ee_max;
+  CHD_CUDA(cudaMalloc((void**)&b->d_samples, B * hb.fo_max * stride * sizeof(double)));
+  CHD_CUDA(cudaMalloc((void**)&b->d_frames, B * sizeof(int)));
+  b->allocs.push_back(b->d_samples);
+  b->allocs.push_back(b->d_frames);
+  CHD_CUDA(cudaMallocHost((void**)&b->h_ipm, B * sizeof(ChdIpm)));
+  *out = b;
+  return 0;
+}
+
+void chd_phys_batch_destroy(chd_phys_batch* b) {
+  if (!b) return;
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->h_ipm) cudaFreeHost(b->h_ipm);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int chd_phys_get_dims(const chd_phys_batch* b, chd_phys_dims* d) {
+  if (!b || !d) return -1;
+  const ChdHostBatch& hb = b->hb;
+  d->batch = hb.B, d->n_max = hb.n_max, d->m_max = hb.m_max, d->slots_max = hb.slots_max, d->n_splines = hb.S;
+  d->p_max = hb.Pmax, d->sets_max = hb.sets_max, d->na_max = hb.Na_max, d->nb_max = hb.nb_max, d->w_max = hb.w_max;
+  d->frames_out_max = hb.fo_max;
+  return 0;
+}
+int chd_phys_get_sizes(const chd_phys_batch* b, int32_t* s) {
+  if (!b || !s) return -1;
+  for (int i = 0; i < b->hb.B; ++i) {
+    const ChdSeq& h = b->hb.seq[i];
+    s[6 * i + 0] = h.n, s[6 * i + 1] = h.m, s[6 * i + 2] = h.nslots, s[6 * i + 3] = h.Na, s[6 * i + 4] = h.nb, s[6 * i + 5] = h.w;
+  }
+  return 0;
+}
+int chd_phys_get_x(const chd_phys_batch* b, double* x) {
+  if (!b || !x) return -1;
+  if (b->host_only) {
+    std::memcpy(x, b->hb.x0.data(), b->hb.x0.size() * sizeof(double));
+    return 0;
+  }
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
+  CHD_CUDA(cudaMemcpy(x, b->D.x, (size_t)b->hb.B * b->hb.n_max * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int chd_phys_set_x(chd_phys_batch* b, const double* x) {
+  if (!b || !x || b->host_only) return -1;
+  CHD_CUDA(cudaMemcpy(b->D.x, x, (size_t)b->hb.B * b->hb.n_max * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int chd_phys_eval(chd_phys_batch* b, int32_t stage, double* cost, double* grad, double* g, double* jac_vals) {
+  if (!b || stage < 0 || stage > 5 || b->host_only) return -1;
+  const ChdHostBatch& hb = b->hb;
+  ChdStageDev sg = stage_dev(hb.stage[stage]);
+  {
+    Timer t(b, KT_INIT);
+    chd_k_stage_begin<<<hb.B, CHD_THREADS, 0, b->stream>>>(b->D, sg, 0);
+  }
+  launch_eval(b, sg, 0);
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
+  CHD_CUDA(cudaGetLastError());
+  const size_t B = hb.B;
+  if (cost) {
+    std::vector<double> c2(2 * B);
+    CHD_CUDA(cudaMemcpy(c2.data(), b->D.cost, 2 * B * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < B; ++i) cost[i] = c2[2 * i];
+  }
+  if (grad) CHD_CUDA(cudaMemcpy(grad, b->D.grad, B * hb.n_max * sizeof(double), cudaMemcpyDeviceToHost));
+  if (g) CHD_CUDA(cudaMemcpy(g, b->D.g, B * hb.m_max * sizeof(double), cudaMemcpyDeviceToHost));
+  if (jac_vals) CHD_CUDA(cudaMemcpy(jac_vals, b->D.Jv, B * hb.slots_max * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int chd_phys_get_layout(const chd_phys_batch* b, int32_t* ent_ptr, int32_t* ent_col, double* row_lo, double* row_hi,
+                        int32_t* row_set, int32_t* var_kkt, int32_t* row_kkt) {
+  if (!b) return -1;
+  const ChdHostBatch& hb = b->hb;
+  if (ent_ptr) std::memcpy(ent_ptr, hb.ent_ptr.data(), hb.ent_ptr.size() * sizeof(int));
+  if (ent_col) std::memcpy(ent_col, hb.ent_col.data(), hb.ent_col.size() * sizeof(int));
+  if (row_lo) std::memcpy(row_lo, hb.row_lo.data(), hb.row_lo.size() * sizeof(double));
+  if (row_hi) std::memcpy(row_hi, hb.row_hi.data(), hb.row_hi.size() * sizeof(double));
+  if (row_set) std::memcpy(row_set, hb.row_set.data(), hb.row_set.size() * sizeof(int));
+  if (var_kkt) std::memcpy(var_kkt, hb.var_kkt.data(), hb.var_kkt.size() * sizeof(int));
+  if (row_kkt) std::memcpy(row_kkt, hb.row_kkt.data(), hb.row_kkt.size() * sizeof(int));
+  return 0;
+}
+
+int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int32_t* status, int32_t* iters, double* stats) {
+  if (!b || stage < 0 || stage > 5 || b->host_only) return -1;
+  const ChdHostBatch& hb = b->hb;
+  ChdStageDev sg = stage_dev(hb.stage[stage]);
+  if (max_iter <= 0) max_iter = hb.stage[stage].max_iter;
+  const int B = hb.B;
+  {
+    Timer t(b, KT_INIT);
+    chd_k_stage_begin<<<B, CHD_THREADS, 0, b->stream>>>(b->D, sg, max_iter);
+  }
+  launch_eval(b, sg, 0);
+  {
+    Timer t(b, KT_INIT);
+    chd_k_init<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
+  }
+  const int check_every = 8;
+  for (int it = 0; it <= max_iter; ++it) {
+    {
+      Timer t(b, KT_KKT);
+      chd_k_kkt<<<B, CHD_THREADS, b->smem_kkt, b->stream>>>(b->D, sg);
+    }
+    {
+      Timer t(b, KT_LS);
+      chd_k_linesearch<<<B, CHD_THREADS, b->smem_ls, b->stream>>>(b->D, sg);
+    }
+    launch_eval(b, sg, 1);
+    if ((it % check_every) == check_every - 1 || it == max_iter) {
+      CHD_CUDA(cudaMemcpyAsync(b->h_ipm, b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost, b->stream));
+      CHD_CUDA(cudaStreamSynchronize(b->stream));
+      bool any = false;
+      for (int i = 0; i < B; ++i) any |= (b->h_ipm[i].status == 1);
+      if (!any) break;
+    }
+  }
+  CHD_CUDA(cudaMemcpyAsync(b->h_ipm, b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost, b->stream));
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
+  CHD_CUDA(cudaGetLastError());
+  for (int i = 0; i < B; ++i) {
+    const ChdIpm& I = b->h_ipm[i];
+    if (status) status[i] = I.status == 1 ? -1 : I.status;
+    if (iters) iters[i] = I.iter;
+    if (stats) {
+      double* s = stats + 8 * i;
+      s[0] = I.f, s[1] = I.E0, s[2] = I.viol_u, s[3] = I.dual_u, s[4] = I.compl_u, s[5] = I.mu, s[6] = I.delta_w, s[7] = I.ls_fail;
+    }
+  }
+  return 0;
+}
+
+int chd_phys_sample_device(chd_phys_batch* b, double* out_device, void* stream) {
+  if (!b || !out_device || b->host_only) return -1;
+  Timer t(b, KT_SAMPLE);
+  chd_k_sample<<<b->hb.B, 128, 0, stream ? (cudaStream_t)stream : b->stream>>>(b->D, out_device, b->d_frames);
+  return 0;
+}
+
+int chd_phys_sample(chd_phys_batch* b, double* out, int32_t* frames_out) {
+  if (!b || !out || b->host_only) return -1;
+  const ChdHostBatch& hb = b->hb;
+  const size_t stride = 6 + 7 * (size_t)hb.n_ee_max, cnt = (size_t)hb.B * hb.fo_max * stride;
+  CHD_CUDA(cudaMemsetAsync(b->d_samples, 0, cnt * sizeof(double), b->stream));
+  int rc = chd_phys_sample_device(b, b->d_samples, nullptr);
+  if (rc) return rc;
+  CHD_CUDA(cudaMemcpyAsync(out, b->d_samples, cnt * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (frames_out) CHD_CUDA(cudaMemcpyAsync(frames_out, b->d_frames, hb.B * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+// Staged schedule of phys_optim.cpp:554-749.  Stage 3 (phase-duration optimisation) is not yet implemented
+// on the device: like the reference when its stage 3 fails (phys_optim.cpp:713-749) the schedule continues
+// with the fixed-duration stage 4 and reports durations_succeed from it.
+int chd_phys_solve(chd_phys_batch* b, double* samples, int32_t* frames_out, int32_t* success, int32_t* stage_status,
+                   int32_t* stage_iters) {
+  if (!b || b->host_only) return -1;
+  const ChdHostBatch& hb = b->hb;
+  const int B = hb.B;
+  const size_t stride = 6 + 7 * (size_t)hb.n_ee_max, snap = (size_t)B * hb.fo_max * stride;
+  std::vector<int32_t> st(B), itn(B);
+  auto run = [&](int stage) -> int {
+    int rc = chd_phys_solve_stage(b, stage, 0, st.data(), itn.data(), nullptr);
+    if (rc) return rc;
+    if (stage_status) std::memcpy(stage_status + (size_t)stage * B, st.data(), B * sizeof(int32_t));
+    if (stage_iters) std::memcpy(stage_iters + (size_t)stage * B, itn.data(), B * sizeof(int32_t));
+    return 0;
+  };
+  int rc;
+  if (stage_status) std::fill(stage_status, stage_status + 6 * (size_t)B, -9);
+  if (stage_iters) std::fill(stage_iters, stage_iters + 6 * (size_t)B, 0);
+  if ((rc = run(CHD_STAGE_11))) return rc;
+  if ((rc = run(CHD_STAGE_12))) return rc;
+  if (samples && (rc = chd_phys_sample(b, samples, frames_out))) return rc;           // sol_out_no_dynamics
+  if ((rc = run(CHD_STAGE_21))) return rc;
+  if ((rc = run(CHD_STAGE_22))) return rc;
+  if (success) for (int i = 0; i < B; ++i) success[2 * i] = st[i] == 0;             // dynamics_succeed (:655)
+  if (samples && (rc = chd_phys_sample(b, samples + snap, frames_out))) return rc;   // sol_out_dynamics
+  if ((rc = run(CHD_STAGE_4))) return rc;
+  if (success) for (int i = 0; i < B; ++i) success[2 * i + 1] = st[i] == 0;         // durations_succeed (:746)
+  if (samples && (rc = chd_phys_sample(b, samples + 2 * snap, frames_out))) return rc;  // sol_out_durations
+  return 0;
+}
+
+int64_t chd_phys_launch_count(const chd_phys_batch* b) { return b ? b->launches : 0; }
+int chd_phys_set_timing(chd_phys_batch* b, int enable) {
+  if (!b) return -1;
+  b->timing = enable;
+  return 0;
+}
+int chd_phys_kernel_times(chd_phys_batch* b, double* ms8, int64_t* launches8, int reset) {
+  if (!b) return -1;
+  for (int i = 0; i < KT_N; ++i) {
+    if (ms8) ms8[i] = b->kt_ms[i];
+    if (launches8) launches8[i] = b->kt_n[i];
+    if (reset) b->kt_ms[i] = 0, b->kt_n[i] = 0;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Device-side views of a phys-optim batch (product code).
+#pragma once
+#include "chd_core.h"
+#include "chd_layout.h"
+
+#define CHD_FILT_MAX 24
+#define CHD_THREADS 256
+
+// row flags
+#define CHD_ROW_ACTIVE 1
+#define CHD_ROW_EQ 2
+#define CHD_ROW_HASL 4
+#define CHD_ROW_HASU 8
+
+// Interior-point state of one sequence ("chd-ipm").
+struct ChdIpm {
+  int status;    // 1 running, 0 converged, -1 iteration cap, -2 numerical failure
+  int iter, nfilt, ls_fail, max_iter, n_bounds, m_act, pad0;
+  double mu, delta_w, sf, theta_max, theta_min, mu_filter, tau;
+  double f, E0, viol_u, dual_u, compl_u;          // error measures at the current iterate
+  double phi0, theta0, dphi, a_pr, a_du;          // line-search inputs produced by the KKT kernel
+  double filt[2 * CHD_FILT_MAX];
+};
+
+struct ChdStageDev {
+  unsigned set_mask;
+  double w_data[3], w_vel[3], w_acc[3];
+};
+
+struct ChdDev {
+  int B, S, Pmax, n_max, m_max, slots_max, sets_max, tab_max, F_max, Kd_max, Kr_max, Na_max, nb_max, w_max, par_stride,
+      n_ee_max, fo_max, Ph_max, win_smem;
+  // ---- static layout ----
+  const ChdSeq* seq;
+  const double *poly_T, *poly_tend, *node_const, *par, *t_dyn, *t_rom, *t_data, *row_lo, *row_hi;
+  const int *node_var, *itab, *ent_ptr, *ent_col, *var_kkt, *row_kkt, *row_set;
+  const ChdSet* sets;
+  const double* phase_tend;                   // B x n_ee_max x Ph_max cumulative phase end times
+  // ---- iterate ----
+  double *x, *xt, *dx, *grad;                 // B x n_max
+  double *g, *gt;                             // B x m_max   (unscaled constraint values at x / trial x)
+  double* Jv;                                 // B x slots_max
+  int* rflag;                                 // B x m_max
+  double *sc, *dL, *dU, *s, *y, *zL, *zU, *ds, *dy, *dzL, *dzU;  // B x m_max
+  double* cost;                               // B x 2 (current, trial)
+  // ---- KKT ----
+  double* Kband;                              // B x Na_max x (w_max+1)   LAPACK lower band, column major
+  double* Kbord;                              // B x Na_max x (nb_max+1)  border rows (+ rhs as the last "row"), column major by band column
+  double* Kcorn;                              // B x (nb_max+1)^2
+  double* sol;                                // B x (Na_max + nb_max)
+  double* scratch;                            // elimination window when it does not fit in shared memory
+  ChdIpm* ipm;                                // B
+};
+
+// IPM constants (oracle/ipm_proto.py Opts; IPOPT defaults unless noted)
+#define CHD_TOL 1e-3            /* phys_optim.cpp:578 */
+#define CHD_CONSTR_VIOL_TOL 1e-4
+#define CHD_DUAL_INF_TOL 1.0
+#define CHD_COMPL_INF_TOL 1e-4
+#define CHD_MU_INIT 0.1
+#define CHD_KAPPA_EPS 10.0
+#define CHD_KAPPA_MU 0.2
+#define CHD_THETA_MU 1.5
+#define CHD_TAU_MIN 0.99
+#define CHD_KAPPA1 1e-2
+#define CHD_KAPPA2 1e-2
+#define CHD_KAPPA_SIGMA 1e10
+#define CHD_S_MAX 100.0
+#define CHD_SCAL_MAX_GRAD 100.0
+#define CHD_BOUND_RELAX 1e-8
+#define CHD_DELTA_W0 1e-4
+#define CHD_DELTA_C 1e-8
+#define CHD_DW_MIN 1e-8
+#define CHD_DW_MAX 1e4
+#define CHD_DW_INC 4.0
+#define CHD_DW_DEC 3.0
+#define CHD_MAX_BACKTRACK 25
+#define CHD_GAMMA_THETA 1e-5
+#define CHD_GAMMA_PHI 1e-5
+#define CHD_S_PHI 2.3
+#define CHD_S_THETA 1.1
+#define CHD_ETA_PHI 1e-8
+#define CHD_INF 1e19

@@ -1,0 +1,122 @@
+/* libchd -- C ABI of the B200-native batched physics-based trajectory optimiser and foot-contact
+ * classifier (drop-in for the hot path of davrempe/contact-human-dynamics).
+ *
+ * Every entry point is plain C: pointers + sizes, int return (0 = ok, negative = error), no exceptions
+ * cross the boundary, no ownership transfer unless stated.  Host pointers are marked [host], device
+ * pointers [device].  All floating point is IEEE fp64 unless the name says otherwise.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   chd_phys_batch_create   <- towr_phys_optim/phys_optim.cpp:380-552  (Read*Info + NlpFormulation::
+ *                              GetVariableSets / GetConstraints, src/nlp_formulation.cpp:79-360)
+ *   chd_phys_solve          <- phys_optim.cpp:554-749  (the five/six staged ifopt::IpoptSolver::Solve calls)
+ *   chd_phys_eval           <- ifopt ConstraintSet::GetValues / FillJacobianBlock and CostTerm::GetCost /
+ *                              FillJacobianBlock as implemented in towr_phys_optim/src/{constraints,costs,models}
+ *   chd_phys_sample         <- SaveSolution, phys_optim.cpp:63-143
+ *   chd_contact_*           <- src/contact_learning/test.py:51-152 (val_full_video) +
+ *                              src/contact_learning/models/openpose_only.py:29-78
+ */
+#ifndef CHD_H_
+#define CHD_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One sequence's inputs, i.e. what phys_optim reads from skel_info.txt, motion_info.txt,
+ * terrain_info.txt and contact_info.txt (phys_optim.cpp:155-267).  End-effector order is the solver's:
+ * L toe, R toe, L heel, R heel (phys_optim.cpp:491-513).  All pointers [host]. */
+typedef struct chd_phys_problem {
+  int32_t n_frames;            /* --nframes */
+  int32_t n_ee;                /* 2 (toes only) or 4 (reference: always 4, phys_optim.cpp:432) */
+  double dt;
+  const double* hip_left;      /* n_frames x 3 */
+  const double* hip_right;     /* n_frames x 3 */
+  double max_leg_length, max_heel_length, heel_dist, body_mass;
+  const double* inertia;       /* n_frames x 6: Ixx Iyy Izz Ixy Ixz Iyz */
+  const double* base_lin;      /* n_frames x 3 */
+  const double* base_ang;      /* n_frames x 3 */
+  const double* ee_pos;        /* n_ee x n_frames x 3 */
+  double floor_normal[3], floor_point[3];
+  const int32_t* ee_start_contact; /* n_ee */
+  const int32_t* ee_n_phases;      /* n_ee */
+  const double* ee_durations;      /* concatenated, sum(ee_n_phases) */
+} chd_phys_problem;
+
+/* gflags of phys_optim.cpp:27-31 */
+typedef struct chd_phys_weights {
+  double w_com_lin, w_com_ang, w_ee, w_smooth, w_dur;
+} chd_phys_weights;
+
+typedef struct chd_phys_batch chd_phys_batch;
+
+/* Stage ids (phys_optim.cpp:554-749): 0 = 1.1, 1 = 1.2, 2 = 2.1, 3 = 2.2, 4 = 3, 5 = 4. */
+enum { CHD_ST_11 = 0, CHD_ST_12 = 1, CHD_ST_21 = 2, CHD_ST_22 = 3, CHD_ST_3 = 4, CHD_ST_4 = 5 };
+
+/* Sizes of the padded batch (strides of every per-sequence array below). */
+typedef struct chd_phys_dims {
+  int32_t batch, n_max, m_max, slots_max, n_splines, p_max, sets_max, na_max, nb_max, w_max, frames_out_max;
+} chd_phys_dims;
+
+/* Builds the NLP layouts of `batch` sequences on the host and uploads them to the current CUDA device.
+ * device < 0 keeps the current device. */
+int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const chd_phys_weights* weights,
+                          int32_t device, chd_phys_batch** out);
+void chd_phys_batch_destroy(chd_phys_batch* b);
+int chd_phys_get_dims(const chd_phys_batch* b, chd_phys_dims* dims);
+/* Per-sequence sizes: n (variables), m (master rows), nslots, Na, nb, w -- six int32 per sequence [host]. */
+int chd_phys_get_sizes(const chd_phys_batch* b, int32_t* sizes6);
+
+/* Current iterate x: batch x n_max doubles.  [host] copies (synchronous). */
+int chd_phys_get_x(const chd_phys_batch* b, double* x_host);
+int chd_phys_set_x(chd_phys_batch* b, const double* x_host);
+
+/* Function-level evaluation at the current x for `stage` (selects active rows and cost weights):
+ *   cost[batch], grad[batch x n_max], g[batch x m_max] (master row order, inactive rows = 0),
+ *   jac_vals[batch x slots_max] (block-row slots; columns via chd_phys_get_layout).  Any output may be NULL.
+ * All outputs [host]. */
+int chd_phys_eval(chd_phys_batch* b, int32_t stage, double* cost, double* grad, double* g, double* jac_vals);
+
+/* Static layout tables, [host] outputs, any may be NULL:
+ *   ent_ptr[batch x (m_max+1)], ent_col[batch x slots_max] (variable index or -1),
+ *   row_lo / row_hi [batch x m_max], row_set[batch x m_max] (constraint-set type of each row),
+ *   var_kkt[batch x n_max], row_kkt[batch x m_max] (KKT ordering; -1 = not an unknown). */
+int chd_phys_get_layout(const chd_phys_batch* b, int32_t* ent_ptr, int32_t* ent_col, double* row_lo, double* row_hi,
+                        int32_t* row_set, int32_t* var_kkt, int32_t* row_kkt);
+
+/* Runs the interior-point solve of one stage for every sequence (warm start from the current x).
+ * status[batch] [host]: 0 = converged (IPOPT "Solve_Succeeded" test), -1 = iteration cap, -2 = numerical failure.
+ * iters[batch] [host], stats[batch x 8] [host]: f, E0, unscaled constraint violation, unscaled dual inf,
+ * unscaled complementarity, mu, delta_w, #line-search failures.  Outputs may be NULL. */
+int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int32_t* status, int32_t* iters,
+                         double* stats);
+
+/* Whole staged schedule of phys_optim.cpp:554-749 for the batch.  `samples` [host]:
+ * 3 x batch x frames_out_max x (6 + 7*n_ee_max) doubles = the three SaveSolution snapshots
+ * (no_dynamics, dynamics, durations), frames_out[batch] [host] = frames per sequence,
+ * success[batch x 2] [host] = (dynamics_succeed, durations_succeed) of success_log.txt.
+ * stage_status [host, 6 x batch] / stage_iters [host, 6 x batch] may be NULL. */
+int chd_phys_solve(chd_phys_batch* b, double* samples, int32_t* frames_out, int32_t* success,
+                   int32_t* stage_status, int32_t* stage_iters);
+
+/* SaveSolution sampling of the current x: out [host] batch x frames_out_max x (6+7*n_ee_max). */
+int chd_phys_sample(chd_phys_batch* b, double* out, int32_t* frames_out);
+
+/* Device-resident variant of the sampler for the multi-GPU gather: writes into a caller-provided
+ * [device] buffer (e.g. an NCCL send buffer) on the given stream (cudaStream_t passed as void*). */
+int chd_phys_sample_device(chd_phys_batch* b, double* out_device, void* stream);
+
+/* Number of kernels launched by this batch so far / reset. */
+int64_t chd_phys_launch_count(const chd_phys_batch* b);
+
+/* Per-kernel accumulated CUDA-event time (ms) and launch counts since the last reset:
+ * names: 0 eval, 1 kkt (assemble+factor+solve), 2 linesearch, 3 init, 4 sample.  [host] arrays of 8. */
+int chd_phys_kernel_times(chd_phys_batch* b, double* ms8, int64_t* launches8, int reset);
+int chd_phys_set_timing(chd_phys_batch* b, int enable);
+
+const char* chd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHD_H_ */

@@ -61,6 +61,9 @@ def lib():
             ("chdo_cons", None, [C.c_void_p, dp]),
             ("chdo_jac", C.c_int, [C.c_void_p, ip, ip, dp]),
             ("chdo_cost_hessian", C.c_int, [C.c_void_p, ip, ip, dp]),
+            ("chdo_lag_hessian", C.c_int, [C.c_void_p, dp, ip, ip, dp]),
+            ("chdo_row_times", None, [C.c_void_p, dp]),
+            ("chdo_var_times", None, [C.c_void_p, dp, dp]),
             ("chdo_sample", C.c_int, [C.c_void_p, dp]),
             ("chdo_spline_point", None, [C.c_void_p, C.c_int, C.c_double, dp]),
             ("chdo_spline_num_polys", C.c_int, [C.c_void_p, C.c_int]),
@@ -182,6 +185,25 @@ class OracleProblem:
         ri, ci, v = np.zeros(nnz, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
         self.L.chdo_cost_hessian(self.h, _ip(ri), _ip(ci), _dp(v))
         return sp.csr_matrix((v, (ri, ci)), shape=(self.n, self.n))
+
+    def lag_hessian(self, y):
+        import scipy.sparse as sp
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        assert y.shape == (self.m,)
+        nnz = self.L.chdo_lag_hessian(self.h, _dp(y), None, None, None)
+        ri, ci, v = np.zeros(nnz, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+        self.L.chdo_lag_hessian(self.h, _dp(y), _ip(ri), _ip(ci), _dp(v))
+        return sp.csr_matrix((v, (ri, ci)), shape=(self.n, self.n))
+
+    def row_times(self):
+        t = np.zeros(self.m)
+        self.L.chdo_row_times(self.h, _dp(t))
+        return t
+
+    def var_times(self):
+        t0, t1 = np.zeros(self.n), np.zeros(self.n)
+        self.L.chdo_var_times(self.h, _dp(t0), _dp(t1))
+        return t0, t1
 
     def sample(self):
         nf = self.L.chdo_sample(self.h, None)

@@ -30,6 +30,12 @@ struct Constraint {
   virtual void values(double* g) const = 0;
   virtual void bounds(double* lo, double* hi) const = 0;
   virtual void jac(Row* r) const = 0;
+  // sum_i y_i * (second derivative model of row i), full symmetric triplets.  Only the terms chd-ipm
+  // keeps: exact bilinear f x (c - p) of the dynamics rows, and y * Jd^T Jd of the
+  // squared-distance rows (leg length, toe-heel distance).  Linear rows contribute nothing.
+  virtual void lag_hessian(const double* y, std::vector<std::array<double, 3>>& trip) const {}
+  // time stamp of every row (layout diagnostics: KKT ordering studies in tests)
+  virtual void row_times(double* t) const = 0;
 };
 struct Cost {
   Problem* P = nullptr;
@@ -51,6 +57,28 @@ static std::vector<double> discretize(double T, double dt) {
   dts.push_back(T);
   return dts;
 }
+
+static void add_outer(std::vector<std::array<double, 3>>& trip, const std::vector<std::pair<int, Vec3>>& cols, double w) {
+  for (auto& a : cols)
+    for (auto& b : cols) {
+      double v = w * dot(a.second, b.second);
+      if (v != 0.0) trip.push_back({(double)a.first, (double)b.first, v});
+    }
+}
+static void gather(std::vector<std::pair<int, Vec3>>& out, const SJac& J, int off, double s) {
+  for (size_t i = 0; i < J.col.size(); ++i) {
+    int c = J.col[i] + off;
+    bool found = false;
+    for (auto& o : out)
+      if (o.first == c) {
+        o.second = o.second + s * J.val[i];
+        found = true;
+        break;
+      }
+    if (!found) out.emplace_back(c, s * J.val[i]);
+  }
+}
+
 
 struct Problem {
   // ---- inputs (phys_optim.cpp:380-417) ----
@@ -288,6 +316,13 @@ struct SplineAcc : Constraint {
   void bounds(double* lo, double* hi) const override {
     for (int i = 0; i < rows; ++i) lo[i] = hi[i] = 0.0;
   }
+  void row_times(double* t) const override {
+    double acc = 0;
+    for (int j = 0; j < nj; ++j) {
+      acc += s->poly_dur[j];
+      for (int d = 0; d < 3; ++d) t[3 * j + d] = acc;
+    }
+  }
   void jac(Row* r) const override {
     for (int j = 0; j < nj; ++j) {
       SJac a0 = s->jac_wrt_nodes(j, s->poly_dur[j], kAcc), a1 = s->jac_wrt_nodes(j + 1, 0.0, kAcc);
@@ -320,6 +355,14 @@ struct Terrain : Constraint {
     for (int id = 1; id < (int)nv.nodes.size(); ++id) {
       lo[id - 1] = 0.0;
       hi[id - 1] = nv.is_constant_node(id) ? 0.0 : 1e20;
+    }
+  }
+  void row_times(double* t) const override {
+    const auto& sp = P->s_motion[ee];
+    double acc = 0;
+    for (int id = 1; id < (int)sp.nv->nodes.size(); ++id) {
+      acc += sp.poly_dur[id - 1];
+      t[id - 1] = acc;
     }
   }
   void jac(Row* r) const override {
@@ -378,6 +421,14 @@ struct Force : Constraint {
       lo[row] = -1e20, hi[row++] = 0.0;
       lo[row] = 0.0, hi[row++] = 1e20;
     }
+  }
+  void row_times(double* t) const override {
+    const auto& sp = P->s_force[ee];
+    std::vector<double> nt(sp.nv->nodes.size(), 0.0);
+    for (size_t i = 1; i < nt.size(); ++i) nt[i] = nt[i - 1] + sp.poly_dur[i - 1];
+    int row = 0;
+    for (int id : ids)
+      for (int k = 0; k < 5; ++k) t[row++] = nt[id];
   }
   void jac(Row* r) const override {
     Vec3 d[5];
@@ -441,6 +492,10 @@ struct Dynamic : Constraint {
   void bounds(double* lo, double* hi) const override {
     for (int i = 0; i < rows; ++i) lo[i] = hi[i] = 0.0;
   }
+  void row_times(double* t) const override {
+    for (size_t k = 0; k < dts.size(); ++k)
+      for (int d = 0; d < 6; ++d) t[6 * k + d] = dts[k];
+  }
   static void put(Row* r, const SJac& J, int off) {  // 3 rows
     for (size_t c = 0; c < J.col.size(); ++c)
       for (int d = 0; d < 3; ++d) r[d].add(J.col[c] + off, J.val[c][d]);
@@ -501,6 +556,35 @@ struct Dynamic : Constraint {
       }
     }
   }
+  // second derivative of  -y_ang . sum_ee f x (c - p)  (bilinear, exact)
+  void lag_hessian(const double* y, std::vector<std::array<double, 3>>& trip) const override {
+    for (size_t k = 0; k < dts.size(); ++k) {
+      double t = dts[k];
+      Vec3 ya{y[6 * k], y[6 * k + 1], y[6 * k + 2]};
+      if (ya[0] == 0.0 && ya[1] == 0.0 && ya[2] == 0.0) continue;
+      SJac Jc = P->s_lin.jac_wrt_nodes(t, kPos);
+      for (int ee = 0; ee < P->n_ee; ++ee) {
+        SJac Jf = P->s_force[ee].jac_wrt_nodes(t, kPos), Jp = P->s_motion[ee].jac_wrt_nodes(t, kPos);
+        for (size_t i = 0; i < Jf.col.size(); ++i) {
+          double uf = Jf.col[i] + P->ee_force[ee].offset;
+          for (size_t j = 0; j < Jc.col.size(); ++j) {
+            double v = -dot(ya, cross(Jf.val[i], Jc.val[j]));
+            if (v == 0.0) continue;
+            double uc = Jc.col[j] + P->base_lin.offset;
+            trip.push_back({uf, uc, v});
+            trip.push_back({uc, uf, v});
+          }
+          for (size_t j = 0; j < Jp.col.size(); ++j) {
+            double v = dot(ya, cross(Jf.val[i], Jp.val[j]));
+            if (v == 0.0) continue;
+            double up = Jp.col[j] + P->ee_motion[ee].offset;
+            trip.push_back({uf, up, v});
+            trip.push_back({up, uf, v});
+          }
+        }
+      }
+    }
+  }
 };
 
 // leg_length_constraint.cpp
@@ -528,6 +612,9 @@ struct LegLength : Constraint {
       g[k] = 0.5 * dot(d, d);
     }
   }
+  void row_times(double* t) const override {
+    for (size_t k = 0; k < dts.size(); ++k) t[k] = dts[k];
+  }
   void bounds(double* lo, double* hi) const override {
     for (int k = 0; k < rows; ++k) lo[k] = 0.0, hi[k] = 0.5 * max_len * max_len;
   }
@@ -539,6 +626,19 @@ struct LegLength : Constraint {
       r[k].add_dT_J(P->euler.deriv_rot_vec_mult(t, h, false), P->base_ang.offset, d, -1.0);
       r[k].add_dT_J(P->s_motion[ee].jac_wrt_nodes(t, kPos), P->ee_motion[ee].offset, d, 1.0);
       if (P->opt_dur) r[k].add_dT_J(P->s_motion[ee].jac_pos_wrt_durations(t), P->dur[ee].offset, d, 1.0);
+    }
+  }
+  void lag_hessian(const double* y, std::vector<std::array<double, 3>>& trip) const override {
+    for (size_t k = 0; k < dts.size(); ++k) {
+      if (y[k] == 0.0) continue;
+      double t = dts[k];
+      Vec3 h = P->hip_at(ee, t);
+      std::vector<std::pair<int, Vec3>> cols;
+      gather(cols, P->s_lin.jac_wrt_nodes(t, kPos), P->base_lin.offset, -1.0);
+      gather(cols, P->euler.deriv_rot_vec_mult(t, h, false), P->base_ang.offset, -1.0);
+      gather(cols, P->s_motion[ee].jac_wrt_nodes(t, kPos), P->ee_motion[ee].offset, 1.0);
+      if (P->opt_dur) gather(cols, P->s_motion[ee].jac_pos_wrt_durations(t), P->dur[ee].offset, 1.0);
+      add_outer(trip, cols, y[k]);
     }
   }
 };
@@ -561,6 +661,9 @@ struct EEDist : Constraint {
       g[k] = 0.5 * dot(d, d);
     }
   }
+  void row_times(double* t) const override {
+    for (size_t k = 0; k < dts.size(); ++k) t[k] = dts[k];
+  }
   void bounds(double* lo, double* hi) const override {
     for (int k = 0; k < rows; ++k) lo[k] = hi[k] = 0.5 * P->heel_dist * P->heel_dist;
   }
@@ -574,6 +677,20 @@ struct EEDist : Constraint {
         r[k].add_dT_J(P->s_motion[e1].jac_pos_wrt_durations(t), P->dur[e1].offset, d, 1.0);
         r[k].add_dT_J(P->s_motion[e2].jac_pos_wrt_durations(t), P->dur[e2].offset, d, -1.0);
       }
+    }
+  }
+  void lag_hessian(const double* y, std::vector<std::array<double, 3>>& trip) const override {
+    for (size_t k = 0; k < dts.size(); ++k) {
+      if (y[k] == 0.0) continue;
+      double t = dts[k];
+      std::vector<std::pair<int, Vec3>> cols;
+      gather(cols, P->s_motion[e1].jac_wrt_nodes(t, kPos), P->ee_motion[e1].offset, 1.0);
+      gather(cols, P->s_motion[e2].jac_wrt_nodes(t, kPos), P->ee_motion[e2].offset, -1.0);
+      if (P->opt_dur) {
+        gather(cols, P->s_motion[e1].jac_pos_wrt_durations(t), P->dur[e1].offset, 1.0);
+        gather(cols, P->s_motion[e2].jac_pos_wrt_durations(t), P->dur[e2].offset, -1.0);
+      }
+      add_outer(trip, cols, y[k]);
     }
   }
 };
@@ -591,6 +708,9 @@ struct Height : Constraint {
   }
   void values(double* g) const override {
     for (size_t k = 0; k < dts.size(); ++k) g[k] = dot(P->normal, P->s_motion[ee].point(dts[k]).p - P->point);
+  }
+  void row_times(double* t) const override {
+    for (size_t k = 0; k < dts.size(); ++k) t[k] = dts[k];
   }
   void bounds(double* lo, double* hi) const override {
     for (int k = 0; k < rows; ++k) lo[k] = 0.0, hi[k] = 1e20;
@@ -617,6 +737,7 @@ struct TotalDuration : Constraint {
     for (int i = 0; i < P->dur[ee].rows(); ++i) s += P->dur[ee].durations[i];
     g[0] = s;
   }
+  void row_times(double* t) const override { t[0] = P->T; }
   void bounds(double* lo, double* hi) const override {
     lo[0] = std::max(0.0, P->T - P->dur_hi);
     hi[0] = P->T - P->dur_lo;
@@ -627,27 +748,6 @@ struct TotalDuration : Constraint {
 };
 
 // ============================================================ costs =============================
-static void add_outer(std::vector<std::array<double, 3>>& trip, const std::vector<std::pair<int, Vec3>>& cols, double w) {
-  for (auto& a : cols)
-    for (auto& b : cols) {
-      double v = w * dot(a.second, b.second);
-      if (v != 0.0) trip.push_back({(double)a.first, (double)b.first, v});
-    }
-}
-static void gather(std::vector<std::pair<int, Vec3>>& out, const SJac& J, int off, double s) {
-  for (size_t i = 0; i < J.col.size(); ++i) {
-    int c = J.col[i] + off;
-    bool found = false;
-    for (auto& o : out)
-      if (o.first == c) {
-        o.second = o.second + s * J.val[i];
-        found = true;
-        break;
-      }
-    if (!found) out.emplace_back(c, s * J.val[i]);
-  }
-}
-
 // data_cost.cpp
 struct DataCost : Cost {
   const Spline* s;
@@ -990,6 +1090,59 @@ int chdo_cost_hessian(void* h, int* ri, int* ci, double* vals) {
     }
   }
   return nnz;
+}
+// Constraint-curvature model sum_i y_i * H_i (see Constraint::lag_hessian).  y has m entries (unscaled rows).
+static int sum_triplets(std::vector<std::array<double, 3>>& trip, int* ri, int* ci, double* vals) {
+  std::sort(trip.begin(), trip.end(), [](auto& a, auto& b) { return a[0] != b[0] ? a[0] < b[0] : a[1] < b[1]; });
+  int nnz = 0, pi = -1, pj = -1;
+  for (auto& t : trip) {
+    int i = (int)t[0], j = (int)t[1];
+    if (i == pi && j == pj) {
+      if (vals) vals[nnz - 1] += t[2];
+    } else {
+      if (vals) ri[nnz] = i, ci[nnz] = j, vals[nnz] = t[2];
+      nnz++;
+      pi = i, pj = j;
+    }
+  }
+  return nnz;
+}
+int chdo_lag_hessian(void* h, const double* y, int* ri, int* ci, double* vals) {
+  Problem* P = (Problem*)h;
+  std::vector<std::array<double, 3>> trip;
+  int r = 0;
+  for (auto& c : P->cons) {
+    c->lag_hessian(y + r, trip);
+    r += c->rows;
+  }
+  return sum_triplets(trip, ri, ci, vals);
+}
+void chdo_row_times(void* h, double* t) {
+  Problem* P = (Problem*)h;
+  int r = 0;
+  for (auto& c : P->cons) {
+    c->row_times(t + r);
+    r += c->rows;
+  }
+}
+// per variable: [t_first, t_last] of the nodes it parameterises (durations: [0, T])
+void chdo_var_times(void* h, double* t0, double* t1) {
+  Problem* P = (Problem*)h;
+  auto fill = [&](const NodesVars& nv, const Spline& sp) {
+    std::vector<double> nt(nv.nodes.size(), 0.0);
+    for (size_t i = 1; i < nt.size(); ++i) nt[i] = nt[i - 1] + sp.poly_dur[i - 1];
+    for (int idx = 0; idx < nv.rows(); ++idx) {
+      double a = 1e300, b = -1e300;
+      for (auto& nvi : nv.index_map[idx]) a = std::min(a, nt[nvi.node]), b = std::max(b, nt[nvi.node]);
+      t0[nv.offset + idx] = a, t1[nv.offset + idx] = b;
+    }
+  };
+  fill(P->base_lin, P->s_lin);
+  fill(P->base_ang, P->s_ang);
+  for (int ee = 0; ee < P->n_ee; ++ee) fill(P->ee_motion[ee], P->s_motion[ee]), fill(P->ee_force[ee], P->s_force[ee]);
+  if (P->opt_dur)
+    for (auto& d : P->dur)
+      for (int i = 0; i < d.rows(); ++i) t0[d.offset + i] = 0, t1[d.offset + i] = P->T;
 }
 // SaveSolution (phys_optim.cpp:63-143): sample all splines at t = 0, dt, ... while t <= T + 1e-5.
 // out layout per frame: base_lin(3) base_ang_deg(3) ee_pos(3*n_ee) ee_force(3*n_ee) contact(n_ee).

@@ -1,0 +1,73 @@
+"""CPU tests of the host-side NLP layout (chd_layout.cpp, reached through the C ABI in host-only mode)
+against the oracle's independent TOWR-style construction."""
+import numpy as np
+import pytest
+
+from tests.util import master_to_oracle_perm
+
+
+@pytest.mark.parametrize("n_ee,seed", [(2, 0), (2, 3), (4, 1)])
+def test_layout_matches_oracle(chd, n_ee, seed):
+    from oracle.phys import OracleProblem
+    p = chd.synth.make_problem(seed, n_ee=n_ee)
+    b = chd.phys.PhysBatch([p], host_only=True)
+    o = OracleProblem(p)
+    o.set_stage("2.2")
+    n, m = b.sizes[0, 0], b.sizes[0, 1]
+    assert n == o.n and m == o.m
+    # initial point (nlp_formulation.cpp:106-203)
+    x0 = b.get_x()[0, :n]
+    xlo, xhi = o.var_bounds()
+    xo = o.get_x()
+    np.testing.assert_allclose(x0, xo, rtol=0, atol=1e-14)
+    lay = b.layout()
+    # fixed variables = equality-bounded ones (start / final base velocity)
+    assert np.array_equal(lay["var_kkt"][0, :n] < 0, xlo == xhi)
+    # row bounds
+    sl = chd.phys.master_row_slices(b, 0, lay)
+    im, io = master_to_oracle_perm(sl, o)
+    cl, cu = o.con_bounds()
+    np.testing.assert_allclose(lay["row_lo"][0, im], cl[io], rtol=0, atol=0)
+    np.testing.assert_allclose(lay["row_hi"][0, im], cu[io], rtol=0, atol=0)
+    # Jacobian pattern: every oracle nonzero is covered by a slot of the same row
+    J = o.jac().tocsr()
+    ptr, col = lay["ent_ptr"][0], lay["ent_col"][0]
+    for rm, ro in zip(im, io):
+        mine = set(col[ptr[rm]:ptr[rm + 1]].tolist())
+        theirs = set(J.indices[J.indptr[ro]:J.indptr[ro + 1]][np.abs(J.data[J.indptr[ro]:J.indptr[ro + 1]]) > 0].tolist())
+        assert theirs <= mine, (rm, ro, sorted(theirs - mine))
+    # KKT ordering: unknowns are a permutation, bandwidth covers every equality coupling
+    Na, nb, w = b.sizes[0, 3], b.sizes[0, 4], b.sizes[0, 5]
+    vk, rk = lay["var_kkt"][0, :n], lay["row_kkt"][0, :m]
+    used = np.concatenate([vk[vk >= 0], rk[rk >= 0]])
+    assert len(np.unique(used)) == len(used) == Na + nb
+    for r in np.nonzero(rk >= 0)[0]:
+        c = col[ptr[r]:ptr[r + 1]]
+        k = vk[c[c >= 0]]
+        k = k[(k >= 0) & (k < Na)]
+        if len(k):
+            assert np.abs(k - rk[r]).max() <= w
+
+
+def test_ragged_batch_padding(chd):
+    ps = [chd.synth.make_problem(s, n_ee=2) for s in range(4)]
+    b = chd.phys.PhysBatch(ps, host_only=True)
+    assert b.dims["batch"] == 4
+    assert b.dims["n_max"] == b.sizes[:, 0].max() and b.dims["m_max"] == b.sizes[:, 1].max()
+    singles = [chd.phys.PhysBatch([p], host_only=True) for p in ps]
+    for i, s in enumerate(singles):
+        assert np.array_equal(s.sizes[0], b.sizes[i])
+        n = s.sizes[0, 0]
+        np.testing.assert_array_equal(s.get_x()[0, :n], b.get_x()[i, :n])
+
+
+def test_library_exports(chd):
+    import ctypes
+    L = ctypes.CDLL(chd.phys.lib_path())
+    for name in chd.phys.EXPORTS:
+        assert hasattr(L, name), name
+    hdr = open(chd.phys.lib_path().replace("contact-human-dynamics_b200/libchd.so", "include/chd.h")).read()
+    import re
+    declared = set(re.findall(r"\b(chd_[a-z_0-9]+)\s*\(", hdr))
+    for name in declared:
+        assert hasattr(L, name), "declared in include/chd.h but not exported: " + name
