@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -42,6 +43,8 @@ struct chd_phys_batch {
   double* d_samples = nullptr;
   size_t smem_eval = 0, smem_kkt = 0, smem_ls = 0;
   ChdIpm* h_ipm = nullptr;  // pinned
+  double* d_x0 = nullptr;
+  int64_t h2d_bytes = 0;
 };
 
 namespace {
@@ -53,6 +56,7 @@ int dev_upload(chd_phys_batch* b, const std::vector<T>& v, const T** out) {
   CHD_CUDA(cudaMalloc(&p, bytes));
   b->allocs.push_back(p);
   if (!v.empty()) CHD_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  b->h2d_bytes += (int64_t)(v.size() * sizeof(T));
   *out = (const T*)p;
   return 0;
 }
@@ -142,7 +146,8 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   AL(cost, B * 2) AL(Kband, B * (size_t)hb.Na_max * (hb.w_max + 1)) AL(Kbord, B * (size_t)hb.Na_max * (hb.nb_max + 1))
   AL(Kcorn, B * (size_t)(hb.nb_max + 1) * (hb.nb_max + 1)) AL(sol, B * (size_t)(hb.Na_max + hb.nb_max)) AL(ipm, B)
 #undef AL
-  CHD_CUDA(cudaMemcpy(D.x, hb.x0.data(), nm * sizeof(double), cudaMemcpyHostToDevice));
+  if ((rc = dev_upload(b, hb.x0, (const double**)&b->d_x0))) return rc;
+  CHD_CUDA(cudaMemcpy(D.x, b->d_x0, nm * sizeof(double), cudaMemcpyDeviceToDevice));
   // shared-memory budgets
   const size_t W = hb.w_max + 1, nbp = hb.nb_max + 1;
   b->smem_eval = (2 * (size_t)hb.n_max + CHD_THREADS) * sizeof(double);
@@ -301,6 +306,7 @@ int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int
       double* s = stats + 8 * i;
       s[0] = I.f, s[1] = I.E0, s[2] = I.viol_u, s[3] = I.dual_u, s[4] = I.compl_u, s[5] = I.mu, s[6] = I.delta_w, s[7] = I.ls_fail;
     }
+    if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "chd prof (Mcycles) seq0 stage %d: err %.2f jasm %.2f hasm %.2f factor %.2f border %.2f back %.2f rec %.2f\n", stage, I.prof[0]/1e6, I.prof[1]/1e6, I.prof[2]/1e6, I.prof[3]/1e6, I.prof[4]/1e6, I.prof[5]/1e6, I.prof[6]/1e6);
   }
   return 0;
 }
@@ -359,6 +365,12 @@ int chd_phys_solve(chd_phys_batch* b, double* samples, int32_t* frames_out, int3
 }
 
 int64_t chd_phys_launch_count(const chd_phys_batch* b) { return b ? b->launches : 0; }
+int64_t chd_phys_h2d_bytes(const chd_phys_batch* b) { return b ? b->h2d_bytes : 0; }
+int chd_phys_reset(chd_phys_batch* b) {
+  if (!b || b->host_only) return -1;
+  CHD_CUDA(cudaMemcpyAsync(b->D.x, b->d_x0, (size_t)b->hb.B * b->hb.n_max * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  return 0;
+}
 int chd_phys_set_timing(chd_phys_batch* b, int enable) {
   if (!b) return -1;
   b->timing = enable;

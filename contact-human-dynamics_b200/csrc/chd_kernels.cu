@@ -69,6 +69,7 @@ __global__ void chd_k_stage_begin(ChdDev D, ChdStageDev sg, int max_iter) {
     I.delta_w = CHD_DELTA_W0;
     I.mu_filter = -1.0;
     I.sf = 1.0;
+    for (int q = 0; q < 8; ++q) I.prof[q] = 0.0;
   }
 }
 
@@ -232,6 +233,8 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_kkt(ChdDev D, ChdStageDev s
   double* bwin = win + (size_t)K.W * K.W;
   const double sf = I.sf;
   double mu = I.mu;
+  long long tk0 = clock64();
+#define CHD_PROF(slot) do { __syncthreads(); if (tid == 0) { long long t_ = clock64(); I.prof[slot] += (double)(t_ - tk0); tk0 = t_; } } while (0)
 
   // ---------------- A. error measures, convergence, barrier update ----------------
   for (int i = tid; i < n; i += nt) vecn[i] = sf * grad[i];
@@ -306,6 +309,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_kkt(ChdDev D, ChdStageDev s
   const double tau = fmax(CHD_TAU_MIN, 1.0 - mu);
   const double delta_w = I.delta_w;
 
+  CHD_PROF(0);
   // ---------------- B. assemble the condensed KKT system ----------------
   const int Na = K.Na, W = K.W, nbp = K.nbp;
   for (size_t i = tid; i < (size_t)Na * W; i += nt) K.band[i] = 0.0;
@@ -371,6 +375,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_kkt(ChdDev D, ChdStageDev s
       }
     }
   }
+  CHD_PROF(1);
   // Hessian model: Gauss-Newton cost Hessian + y^+ * Jd^T Jd of the squared-distance rows
   {
     ChdCtx c;
@@ -454,6 +459,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_kkt(ChdDev D, ChdStageDev s
   }
   __threadfence_block();
   __syncthreads();
+  CHD_PROF(2);
 
   // ---------------- C. band LDL^T with dense border (right-looking, shared-memory window) ----------------
   // window column slot = column % W; bwin[slot*nbp + r] border rows (r < nbl) and rhs (r = NBR)
@@ -506,6 +512,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_kkt(ChdDev D, ChdStageDev s
     }
     __syncthreads();
   }
+  CHD_PROF(3);
   // dense Cholesky of the border Schur complement S = cc[0..nbl)^2 and solve S xb = rb (rb = row NBR of cc)
   for (int k = 0; k < nbl; ++k) {
     const double dk = cc[k * nbp + k];
@@ -531,6 +538,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_kkt(ChdDev D, ChdStageDev s
   __syncthreads();
   double* sol = D.sol + (size_t)b * (D.Na_max + D.nb_max);
   for (int i = tid; i < nbl; i += nt) sol[Na + i] = xw[W + i];
+  CHD_PROF(4);
   // backward substitution on the band: x_k = u_k - sum_i L[k+i][k] x_{k+i} - sum_b Lb[b][k] xb
   // chunks of CH columns are staged in shared memory by all threads, then swept by warp 0
   {
@@ -571,6 +579,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_kkt(ChdDev D, ChdStageDev s
   }
   __syncthreads();
 
+  CHD_PROF(5);
   // ---------------- D. recover the full step, fraction-to-the-boundary, line-search inputs ----------------
   double* dx = D.dx + vo;
   for (int i = tid; i < n; i += nt) {
@@ -622,6 +631,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_kkt(ChdDev D, ChdStageDev s
     I.a_pr = a_pr, I.a_du = a_du, I.dphi = dphi;
     I.phi0 = sf * D.cost[2 * b] + phib;
   }
+  CHD_PROF(6);
 }
 
 // ------------------------------------------------------------------ line search -------------------

@@ -49,7 +49,7 @@ class _Dims(C.Structure):
 EXPORTS = ["chd_version", "chd_phys_batch_create", "chd_phys_batch_destroy", "chd_phys_get_dims", "chd_phys_get_sizes",
            "chd_phys_get_x", "chd_phys_set_x", "chd_phys_eval", "chd_phys_get_layout", "chd_phys_solve_stage",
            "chd_phys_solve", "chd_phys_sample", "chd_phys_sample_device", "chd_phys_launch_count",
-           "chd_phys_kernel_times", "chd_phys_set_timing"]
+           "chd_phys_kernel_times", "chd_phys_set_timing", "chd_phys_h2d_bytes", "chd_phys_reset"]
 
 
 def lib_path() -> str:
@@ -84,6 +84,9 @@ def load_lib():
         L.chd_phys_launch_count.argtypes = [vp]
         L.chd_phys_kernel_times.argtypes = [vp, vp, vp, C.c_int]
         L.chd_phys_set_timing.argtypes = [vp, C.c_int]
+        L.chd_phys_h2d_bytes.argtypes = [vp]
+        L.chd_phys_h2d_bytes.restype = C.c_int64
+        L.chd_phys_reset.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -224,6 +227,12 @@ class PhysBatch:
     # ---- instrumentation -----------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.L.chd_phys_launch_count(self.h))
+
+    def h2d_bytes(self) -> int:
+        return int(self.L.chd_phys_h2d_bytes(self.h))
+
+    def reset(self):
+        self._chk(self.L.chd_phys_reset(self.h))
 
     def set_timing(self, on: bool):
         self.L.chd_phys_set_timing(self.h, int(on))

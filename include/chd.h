@@ -106,8 +106,12 @@ int chd_phys_sample(chd_phys_batch* b, double* out, int32_t* frames_out);
  * [device] buffer (e.g. an NCCL send buffer) on the given stream (cudaStream_t passed as void*). */
 int chd_phys_sample_device(chd_phys_batch* b, double* out_device, void* stream);
 
-/* Number of kernels launched by this batch so far / reset. */
+/* Number of kernels launched by this batch so far. */
 int64_t chd_phys_launch_count(const chd_phys_batch* b);
+/* Bytes copied host -> device by chd_phys_batch_create (problem data + layout tables). */
+int64_t chd_phys_h2d_bytes(const chd_phys_batch* b);
+/* Restores the initial point of nlp_formulation.cpp:106-203 on the device (no host traffic). */
+int chd_phys_reset(chd_phys_batch* b);
 
 /* Per-kernel accumulated CUDA-event time (ms) and launch counts since the last reset:
  * names: 0 eval, 1 kkt (assemble+factor+solve), 2 linesearch, 3 init, 4 sample.  [host] arrays of 8. */

@@ -1,0 +1,506 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle of the interior-point loop ("chd-ipm", DESIGN.md section IPM).
+//
+// Single-threaded C++ restatement of oracle/ipm_proto.py: IPOPT's primal-dual barrier framework (slack
+// reformulation, fraction-to-the-boundary, monotone barrier update, scaled optimality error and
+// termination test of phys_optim.cpp:568-578's options, gradient-based scaling) with a Gauss-Newton
+// Hessian model, Levenberg-Marquardt regularisation and a filter line search without restoration.
+// It is generic over the NLP callbacks of towr_problem.cpp (the role ifopt plays for IPOPT) and solves
+// the condensed KKT system with an unpivoted banded LDL^T plus dense border -- written independently of
+// the CUDA implementation (row-oriented storage, scalar loops).
+//
+// PARITY UNPINNED: the reference's own solver stack (IPOPT + MA57 + L-BFGS) cannot be built offline; this
+// oracle pins the CUDA solver to the same algorithm run on the CPU, not to IPOPT iterates.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+extern "C" {
+void chdo_set_stage(void* h, int st);
+int chdo_n(void* h);
+int chdo_m(void* h);
+void chdo_get_x(void* h, double* x);
+void chdo_set_x(void* h, const double* x);
+void chdo_var_bounds(void* h, double* lo, double* hi);
+int chdo_num_constraint_sets(void* h);
+int chdo_constraint_set_rows(void* h, int i);
+const char* chdo_constraint_set_name(void* h, int i);
+void chdo_con_bounds(void* h, double* lo, double* hi);
+double chdo_cost(void* h);
+void chdo_grad(void* h, double* g);
+void chdo_cons(void* h, double* g);
+int chdo_jac(void* h, int* ri, int* ci, double* vals);
+int chdo_cost_hessian(void* h, int* ri, int* ci, double* vals);
+int chdo_lag_hessian(void* h, const double* y, int* ri, int* ci, double* vals);
+void chdo_row_times(void* h, double* t);
+void chdo_var_times(void* h, double* t0, double* t1);
+}
+
+namespace {
+
+const double kInf = 1e19;
+struct Opts {
+  double tol = 1e-3, constr_viol_tol = 1e-4, dual_inf_tol = 1.0, compl_inf_tol = 1e-4;
+  double mu_init = 0.1, kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
+  double kappa1 = 1e-2, kappa2 = 1e-2, kappa_sigma = 1e10, s_max = 100.0, scal_max_grad = 100.0, bound_relax = 1e-8;
+  double delta_w0 = 1e-4, delta_c = 1e-8, dw_min = 1e-8, dw_max = 1e4, dw_inc = 4.0, dw_dec = 3.0;
+  int max_backtrack = 25;
+  double gamma_theta = 1e-5, gamma_phi = 1e-5, s_phi = 2.3, s_theta = 1.1, eta_phi = 1e-8;
+  int filt_max = 24;
+};
+
+struct Triplets {
+  std::vector<int> r, c;
+  std::vector<double> v;
+};
+
+// symmetric arrowhead matrix: band part (row-major, row i holds columns i-w..i) + dense border rows
+struct Arrow {
+  int Na = 0, nb = 0, w = 0;
+  std::vector<double> band, bord, corn, rhs;  // band[i*(w+1) + (w-(i-j))], bord[b*Na + j], corn[b*nb + b2] (lower), rhs[Na+nb]
+  void init(int Na_, int nb_, int w_) {
+    Na = Na_, nb = nb_, w = w_;
+    band.assign((size_t)Na * (w + 1), 0.0);
+    bord.assign((size_t)nb * Na, 0.0);
+    corn.assign((size_t)nb * nb, 0.0);
+    rhs.assign(Na + nb, 0.0);
+  }
+  void add(int i, int j, double v) {
+    if (i < j) std::swap(i, j);
+    if (i < Na) band[(size_t)i * (w + 1) + (w - (i - j))] += v;
+    else if (j < Na) bord[(size_t)(i - Na) * Na + j] += v;
+    else corn[(size_t)(i - Na) * nb + (j - Na)] += v;
+  }
+  // in-place LDL^T without pivoting and solve; returns false on a zero / non-finite pivot
+  bool solve(std::vector<double>& x) {
+    const int W = w + 1;
+    auto A = [&](int i, int j) -> double& { return band[(size_t)i * W + (w - (i - j))]; };
+    std::vector<double> z(rhs);
+    for (int k = 0; k < Na; ++k) {
+      const double d = A(k, k);
+      if (!(std::fabs(d) > 1e-300) || !std::isfinite(d)) { if (getenv("CHDO_DEBUG")) fprintf(stderr, "band pivot %d = %g\n", k, d); return false; }
+      const int lim = std::min(w, Na - 1 - k);
+      // column k of L in the band
+      for (int i = k + 1; i <= k + lim; ++i) {
+        const double aik = A(i, k);
+        if (aik == 0.0) continue;
+        const double l = aik / d;
+        for (int j = k + 1; j <= i; ++j) A(i, j) -= l * A(j, k);
+        z[i] -= l * z[k];
+      }
+      for (int b = 0; b < nb; ++b) {
+        const double abk = bord[(size_t)b * Na + k];
+        if (abk == 0.0) continue;
+        const double l = abk / d;
+        for (int j = k + 1; j <= k + lim; ++j) bord[(size_t)b * Na + j] -= l * A(j, k);
+        for (int b2 = 0; b2 <= b; ++b2) corn[(size_t)b * nb + b2] -= l * bord[(size_t)b2 * Na + k];
+        z[Na + b] -= l * z[k];
+      }
+      // store scaled column (after all updates that use the unscaled values)
+      for (int i = k + 1; i <= k + lim; ++i) A(i, k) /= d;
+      for (int b = 0; b < nb; ++b) bord[(size_t)b * Na + k] /= d;
+    }
+    // border Schur complement: LDL^T of corn
+    for (int k = 0; k < nb; ++k) {
+      const double d = corn[(size_t)k * nb + k];
+      if (!(d > 0.0) || !std::isfinite(d)) { if (getenv("CHDO_DEBUG")) fprintf(stderr, "border pivot %d = %g\n", k, d); return false; }
+      for (int i = k + 1; i < nb; ++i) {
+        const double l = corn[(size_t)i * nb + k] / d;
+        for (int j = k + 1; j <= i; ++j) corn[(size_t)i * nb + j] -= l * corn[(size_t)j * nb + k];
+        z[Na + i] -= l * z[Na + k];
+      }
+      for (int i = k + 1; i < nb; ++i) corn[(size_t)i * nb + k] /= d;  // scale after the unscaled column was used
+    }
+    x.assign(Na + nb, 0.0);
+    for (int k = nb - 1; k >= 0; --k) {
+      double v = z[Na + k] / corn[(size_t)k * nb + k];
+      for (int i = k + 1; i < nb; ++i) v -= corn[(size_t)i * nb + k] * x[Na + i];
+      x[Na + k] = v;
+    }
+    for (int k = Na - 1; k >= 0; --k) {
+      double v = z[k] / A(k, k);
+      const int lim = std::min(w, Na - 1 - k);
+      for (int i = k + 1; i <= k + lim; ++i) v -= A(i, k) * x[i];
+      for (int b = 0; b < nb; ++b) v -= bord[(size_t)b * Na + k] * x[Na + b];
+      x[k] = v;
+    }
+    return true;
+  }
+};
+
+struct Solver {
+  void* h;
+  Opts o;
+  int n = 0, m = 0;
+  std::vector<double> xlo, xhi, cl, cu;
+  std::vector<char> fixed, eq, hasL, hasU, dist_row;
+  std::vector<int> vk, rk;  // KKT ordering
+  int Na = 0, nb = 0, w = 0;
+  // CSR Jacobian
+  std::vector<int> jp, jc;
+  std::vector<double> jv;
+
+  void eval_jac() {
+    int nnz = chdo_jac(h, nullptr, nullptr, nullptr);
+    std::vector<int> ri(nnz), ci(nnz);
+    jv.assign(nnz, 0.0);
+    chdo_jac(h, ri.data(), ci.data(), jv.data());
+    jp.assign(m + 1, 0);
+    for (int k = 0; k < nnz; ++k) jp[ri[k] + 1]++;
+    for (int r = 0; r < m; ++r) jp[r + 1] += jp[r];
+    jc = ci;  // triplets are row sorted
+  }
+  Triplets hess(bool cost, const double* y) {
+    Triplets t;
+    int nnz = cost ? chdo_cost_hessian(h, nullptr, nullptr, nullptr) : chdo_lag_hessian(h, y, nullptr, nullptr, nullptr);
+    t.r.resize(nnz), t.c.resize(nnz), t.v.resize(nnz);
+    if (cost) chdo_cost_hessian(h, t.r.data(), t.c.data(), t.v.data());
+    else chdo_lag_hessian(h, y, t.r.data(), t.c.data(), t.v.data());
+    return t;
+  }
+
+  void ordering() {
+    // time-sorted band; variables that live longer than 0.15 s (stance positions) go to the border
+    std::vector<double> t0(n), t1(n), rt(m);
+    chdo_var_times(h, t0.data(), t1.data());
+    chdo_row_times(h, rt.data());
+    struct Key {
+      double t;
+      int kind, id;
+    };
+    std::vector<Key> keys;
+    std::vector<int> border;
+    vk.assign(n, -1);
+    rk.assign(m, -1);
+    for (int v = 0; v < n; ++v) {
+      if (fixed[v]) continue;
+      if (t1[v] - t0[v] > 0.15) border.push_back(v);
+      else keys.push_back({0.5 * (t0[v] + t1[v]), 0, v});
+    }
+    for (int r = 0; r < m; ++r)
+      if (eq[r]) keys.push_back({rt[r] + 1e-6, 1, r});
+    std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.t < b.t; });
+    for (size_t i = 0; i < keys.size(); ++i) (keys[i].kind == 0 ? vk[keys[i].id] : rk[keys[i].id]) = (int)i;
+    Na = (int)keys.size();
+    nb = (int)border.size();
+    for (int j = 0; j < nb; ++j) vk[border[j]] = Na + j;
+  }
+  // half bandwidth needed by the current patterns
+  int bandwidth(const Triplets& W1, const Triplets& W2) {
+    int bw = 0;
+    auto upd = [&](int a, int b) {
+      if (a < 0 || b < 0 || a >= Na || b >= Na) return;
+      bw = std::max(bw, std::abs(a - b));
+    };
+    for (int r = 0; r < m; ++r) {
+      if (eq[r]) {
+        for (int e = jp[r]; e < jp[r + 1]; ++e) upd(rk[r], vk[jc[e]]);
+      } else {
+        int lo = 1 << 30, hi = -1;
+        for (int e = jp[r]; e < jp[r + 1]; ++e) {
+          int k = vk[jc[e]];
+          if (k >= 0 && k < Na) lo = std::min(lo, k), hi = std::max(hi, k);
+        }
+        if (hi >= 0) bw = std::max(bw, hi - lo);
+      }
+    }
+    for (size_t k = 0; k < W1.v.size(); ++k) upd(vk[W1.r[k]], vk[W1.c[k]]);
+    for (size_t k = 0; k < W2.v.size(); ++k) upd(vk[W2.r[k]], vk[W2.c[k]]);
+    return bw;
+  }
+
+  int run(int stage, int max_iter, double* stats, int verbose) {
+    chdo_set_stage(h, stage);
+    n = chdo_n(h), m = chdo_m(h);
+    std::vector<double> x(n);
+    chdo_get_x(h, x.data());
+    xlo.assign(n, 0), xhi.assign(n, 0);
+    chdo_var_bounds(h, xlo.data(), xhi.data());
+    fixed.assign(n, 0);
+    for (int i = 0; i < n; ++i)
+      if (xlo[i] == xhi[i]) fixed[i] = 1, x[i] = xlo[i];
+    cl.assign(m, 0), cu.assign(m, 0);
+    chdo_con_bounds(h, cl.data(), cu.data());
+    eq.assign(m, 0), hasL.assign(m, 0), hasU.assign(m, 0), dist_row.assign(m, 0);
+    for (int r = 0; r < m; ++r) {
+      eq[r] = cl[r] == cu[r];
+      hasL[r] = !eq[r] && cl[r] > -kInf;
+      hasU[r] = !eq[r] && cu[r] < kInf;
+    }
+    {
+      int off = 0;
+      for (int i = 0; i < chdo_num_constraint_sets(h); ++i) {
+        std::string nm = chdo_constraint_set_name(h, i);
+        int rows = chdo_constraint_set_rows(h, i);
+        if (nm.rfind("leg-length", 0) == 0 || nm.rfind("ee-dist", 0) == 0)
+          for (int r = off; r < off + rows; ++r) dist_row[r] = 1;
+        off += rows;
+      }
+    }
+    ordering();
+    auto evaluate = [&](const std::vector<double>& xx, double& f, std::vector<double>& c) {
+      chdo_set_x(h, xx.data());
+      f = chdo_cost(h);
+      c.resize(m);
+      chdo_cons(h, c.data());
+    };
+    double f;
+    std::vector<double> c, g(n);
+    evaluate(x, f, c);
+    chdo_grad(h, g.data());
+    eval_jac();
+    // gradient based scaling
+    double gmax = 0;
+    for (int i = 0; i < n; ++i)
+      if (!fixed[i]) gmax = std::max(gmax, std::fabs(g[i]));
+    const double sf = gmax > o.scal_max_grad ? o.scal_max_grad / gmax : 1.0;
+    std::vector<double> sc(m, 1.0), dL(m), dU(m), s(m), y(m, 0.0), zL(m, 0.0), zU(m, 0.0);
+    int n_bounds = 0;
+    for (int r = 0; r < m; ++r) {
+      double rm = 0;
+      for (int e = jp[r]; e < jp[r + 1]; ++e)
+        if (!fixed[jc[e]]) rm = std::max(rm, std::fabs(jv[e]));
+      sc[r] = std::max(rm > o.scal_max_grad ? o.scal_max_grad / rm : 1.0, 1e-8);
+      const double lo = cl[r] * sc[r], hi = cu[r] * sc[r], d = sc[r] * c[r];
+      if (eq[r]) {
+        dL[r] = lo, dU[r] = hi, s[r] = d;
+        continue;
+      }
+      dL[r] = hasL[r] ? lo - o.bound_relax * std::max(1.0, std::fabs(lo)) : -INFINITY;
+      dU[r] = hasU[r] ? hi + o.bound_relax * std::max(1.0, std::fabs(hi)) : INFINITY;
+      double sv = d;
+      if (hasL[r]) {
+        double pL = o.kappa1 * std::max(1.0, std::fabs(dL[r]));
+        if (hasU[r]) pL = std::min(pL, o.kappa2 * (dU[r] - dL[r]));
+        sv = std::max(sv, dL[r] + pL);
+      }
+      if (hasU[r]) {
+        double pU = o.kappa1 * std::max(1.0, std::fabs(dU[r]));
+        if (hasL[r]) pU = std::min(pU, o.kappa2 * (dU[r] - dL[r]));
+        sv = std::min(sv, dU[r] - pU);
+      }
+      s[r] = sv;
+      zL[r] = hasL[r] ? 1.0 : 0.0;
+      zU[r] = hasU[r] ? 1.0 : 0.0;
+      n_bounds += hasL[r] + hasU[r];
+    }
+    double mu = o.mu_init, delta_w = o.delta_w0, mu_filter = -1.0, theta_max = 0, theta_min = 0;
+    const double mu_min = std::min(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
+    std::vector<std::pair<double, double>> filt;
+    int status = -1, it = 0, ls_fail = 0;
+    double E0 = 0, violu = 0, dual_u = 0, compl_u = 0;
+    std::vector<double> rx(n), dx(n), ds(m), dy(m), dzL(m), dzU(m), sol, ypos(m), xt(n), ct;
+    Arrow K;
+    for (it = 0;; ++it) {
+      // ---- error measures ----
+      for (int i = 0; i < n; ++i) rx[i] = sf * g[i];
+      double ysum = 0, zsum = 0, cviol = 0, theta = 0, rs = 0, cmax = -INFINITY, cmin = INFINITY;
+      violu = 0;
+      for (int r = 0; r < m; ++r) {
+        const double d = sc[r] * c[r];
+        ysum += std::fabs(y[r]);
+        violu = std::max(violu, std::max(cl[r] - c[r], c[r] - cu[r]));
+        const double ys = sc[r] * y[r];
+        for (int e = jp[r]; e < jp[r + 1]; ++e) rx[jc[e]] += ys * jv[e];
+        if (eq[r]) {
+          const double re = d - dL[r];
+          cviol = std::max(cviol, std::fabs(re)), theta += std::fabs(re);
+        } else {
+          const double ri = d - s[r];
+          cviol = std::max(cviol, std::fabs(ri)), theta += std::fabs(ri);
+          rs = std::max(rs, std::fabs(-y[r] - zL[r] + zU[r]));
+          zsum += zL[r] + zU[r];
+          if (hasL[r]) { double cp = (s[r] - dL[r]) * zL[r]; cmax = std::max(cmax, cp), cmin = std::min(cmin, cp); }
+          if (hasU[r]) { double cp = (dU[r] - s[r]) * zU[r]; cmax = std::max(cmax, cp), cmin = std::min(cmin, cp); }
+        }
+      }
+      violu = std::max(violu, 0.0);
+      double dual_inf = rs;
+      for (int i = 0; i < n; ++i)
+        if (!fixed[i]) dual_inf = std::max(dual_inf, std::fabs(rx[i]));
+      const double s_d = std::max(o.s_max, (ysum + zsum) / std::max((double)(m + n_bounds), 1.0)) / o.s_max;
+      const double s_c = std::max(o.s_max, zsum / std::max((double)n_bounds, 1.0)) / o.s_max;
+      auto compl_err = [&](double mm) { return n_bounds > 0 ? std::max(std::fabs(cmax - mm), std::fabs(cmin - mm)) : 0.0; };
+      E0 = std::max(std::max(dual_inf / s_d, cviol), compl_err(0.0) / s_c);
+      dual_u = dual_inf / sf, compl_u = compl_err(0.0) / sf;
+      if (verbose) printf("it %3d f %.6e E0 %.2e viol %.2e dual %.2e mu %.1e dw %.1e\n", it, f, E0, violu, dual_inf, mu, delta_w);
+      if (E0 <= o.tol && violu <= o.constr_viol_tol && dual_u <= o.dual_inf_tol && compl_u <= o.compl_inf_tol) {
+        status = 0;
+        break;
+      }
+      if (it >= max_iter) {
+        status = -1;
+        break;
+      }
+      while (true) {
+        const double Emu = std::max(std::max(dual_inf / s_d, cviol), compl_err(mu) / s_c);
+        if (Emu <= o.kappa_eps * mu && mu > mu_min) mu = std::max(mu_min, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
+        else break;
+      }
+      const double tau = std::max(o.tau_min, 1.0 - mu);
+      if (it == 0) theta_max = 1e4 * std::max(1.0, theta), theta_min = 1e-4 * std::max(1.0, theta);
+      if (mu != mu_filter) filt.clear(), mu_filter = mu;
+      // ---- condensed KKT ----
+      for (int r = 0; r < m; ++r) ypos[r] = dist_row[r] ? std::max(sc[r] * y[r], 0.0) : 0.0;
+      Triplets W1 = hess(true, nullptr), W2 = hess(false, ypos.data());
+      w = bandwidth(W1, W2);
+      K.init(Na, nb, w);
+      for (int i = 0; i < n; ++i)
+        if (vk[i] >= 0) K.add(vk[i], vk[i], delta_w), K.rhs[vk[i]] += -sf * g[i];
+      for (size_t k = 0; k < W1.v.size(); ++k) {
+        int a = vk[W1.r[k]], b = vk[W1.c[k]];
+        if (a >= 0 && b >= 0 && a >= b) K.add(a, b, sf * W1.v[k]);
+      }
+      for (size_t k = 0; k < W2.v.size(); ++k) {
+        int a = vk[W2.r[k]], b = vk[W2.c[k]];
+        if (a >= 0 && b >= 0 && a >= b) K.add(a, b, W2.v[k]);
+      }
+      for (int r = 0; r < m; ++r) {
+        if (eq[r]) {
+          K.add(rk[r], rk[r], -o.delta_c);
+          K.rhs[rk[r]] += -(sc[r] * c[r] - dL[r]);
+          for (int e = jp[r]; e < jp[r + 1]; ++e) {
+            int kc = vk[jc[e]];
+            if (kc < 0) continue;
+            K.add(rk[r], kc, sc[r] * jv[e]);
+            K.rhs[kc] += -sc[r] * y[r] * jv[e];
+          }
+        } else {
+          const double gapL = hasL[r] ? s[r] - dL[r] : 1.0, gapU = hasU[r] ? dU[r] - s[r] : 1.0;
+          const double Sig = (hasL[r] ? zL[r] / gapL : 0.0) + (hasU[r] ? zU[r] / gapU : 0.0);
+          const double bvec = (hasL[r] ? mu / gapL : 0.0) - (hasU[r] ? mu / gapU : 0.0);
+          const double coef = Sig * (sc[r] * c[r] - s[r]) - bvec;
+          for (int ea = jp[r]; ea < jp[r + 1]; ++ea) {
+            int ka = vk[jc[ea]];
+            if (ka < 0) continue;
+            const double va = sc[r] * jv[ea];
+            K.rhs[ka] += -va * coef;
+            for (int eb = jp[r]; eb < jp[r + 1]; ++eb) {
+              int kb = vk[jc[eb]];
+              if (kb < 0 || ka < kb) continue;
+              K.add(ka, kb, Sig * va * sc[r] * jv[eb]);
+            }
+          }
+        }
+      }
+      const bool ok = K.solve(sol);
+      if (!ok) {
+        delta_w = std::min(std::max(delta_w * 100.0, 1e-4), o.dw_max * 10);
+        ls_fail++;
+        if (delta_w > o.dw_max) {
+          status = -2;
+          break;
+        }
+        continue;
+      }
+      // ---- step recovery ----
+      for (int i = 0; i < n; ++i) dx[i] = vk[i] >= 0 ? sol[vk[i]] : 0.0;
+      double a_pr = 1.0, a_du = 1.0, dphi = 0, phib = 0;
+      for (int i = 0; i < n; ++i) dphi += sf * g[i] * dx[i];
+      for (int r = 0; r < m; ++r) {
+        if (eq[r]) {
+          dy[r] = sol[rk[r]], ds[r] = 0;
+          continue;
+        }
+        double Jdx = 0;
+        for (int e = jp[r]; e < jp[r + 1]; ++e) Jdx += jv[e] * dx[jc[e]];
+        const double dsr = sc[r] * Jdx + (sc[r] * c[r] - s[r]);
+        const double gapL = hasL[r] ? s[r] - dL[r] : 1.0, gapU = hasU[r] ? dU[r] - s[r] : 1.0;
+        const double sigL = hasL[r] ? zL[r] / gapL : 0.0, sigU = hasU[r] ? zU[r] / gapU : 0.0;
+        const double bvec = (hasL[r] ? mu / gapL : 0.0) - (hasU[r] ? mu / gapU : 0.0);
+        ds[r] = dsr;
+        dy[r] = (sigL + sigU) * dsr - y[r] - bvec;
+        dzL[r] = hasL[r] ? mu / gapL - zL[r] - sigL * dsr : 0.0;
+        dzU[r] = hasU[r] ? mu / gapU - zU[r] + sigU * dsr : 0.0;
+        if (hasL[r] && dsr < 0) a_pr = std::min(a_pr, -tau * gapL / dsr);
+        if (hasU[r] && dsr > 0) a_pr = std::min(a_pr, tau * gapU / dsr);
+        if (hasL[r] && dzL[r] < 0) a_du = std::min(a_du, -tau * zL[r] / dzL[r]);
+        if (hasU[r] && dzU[r] < 0) a_du = std::min(a_du, -tau * zU[r] / dzU[r]);
+        if (hasL[r]) dphi -= mu * dsr / gapL, phib -= mu * std::log(gapL);
+        if (hasU[r]) dphi += mu * dsr / gapU, phib -= mu * std::log(gapU);
+      }
+      const double phi0 = sf * f + phib;
+      // ---- filter line search ----
+      double alpha = a_pr, ft = f;
+      bool accepted = false, ftype = false;
+      int ls = 0;
+      for (ls = 0; ls < o.max_backtrack; ++ls) {
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + alpha * dx[i];
+        evaluate(xt, ft, ct);
+        double theta_t = 0, bar = 0;
+        for (int r = 0; r < m; ++r) {
+          const double d = sc[r] * ct[r];
+          if (eq[r]) theta_t += std::fabs(d - dL[r]);
+          else {
+            const double st = s[r] + alpha * ds[r];
+            theta_t += std::fabs(d - st);
+            if (hasL[r]) bar -= mu * std::log(st - dL[r]);
+            if (hasU[r]) bar -= mu * std::log(dU[r] - st);
+          }
+        }
+        const double phit = sf * ft + bar;
+        bool okp = std::isfinite(phit) && std::isfinite(theta_t) && theta_t <= theta_max;
+        for (auto& e : filt)
+          if (okp && theta_t >= e.first && phit >= e.second) okp = false;
+        if (okp) {
+          const bool switching = dphi < 0 && alpha * std::pow(-dphi, o.s_phi) > std::pow(theta, o.s_theta);
+          const bool armijo = phit <= phi0 + o.eta_phi * alpha * dphi;
+          if (theta <= theta_min && switching) {
+            if (armijo) accepted = true, ftype = true;
+          } else if (theta_t <= (1 - o.gamma_theta) * theta || phit <= phi0 - o.gamma_phi * theta) {
+            accepted = true;
+            ftype = switching && armijo;
+          }
+        }
+        if (accepted) break;
+        alpha *= 0.5;
+      }
+      if (!accepted) {
+        alpha *= 2.0;
+        ls = o.max_backtrack;
+        ls_fail++;
+      }
+      if (accepted && !ftype && (int)filt.size() < o.filt_max) filt.emplace_back((1 - o.gamma_theta) * theta, phi0 - o.gamma_phi * theta);
+      if (ls == 0) delta_w = std::max(delta_w / o.dw_dec, o.dw_min);
+      else delta_w = std::min(delta_w * std::pow(o.dw_inc, (double)std::min(ls, 3)), o.dw_max);
+      x = xt;
+      for (int r = 0; r < m; ++r) {
+        y[r] += alpha * dy[r];
+        if (eq[r]) continue;
+        s[r] += alpha * ds[r];
+        if (hasL[r]) {
+          const double gap = s[r] - dL[r];
+          zL[r] = std::min(std::max(zL[r] + a_du * dzL[r], mu / (o.kappa_sigma * gap)), o.kappa_sigma * mu / gap);
+        }
+        if (hasU[r]) {
+          const double gap = dU[r] - s[r];
+          zU[r] = std::min(std::max(zU[r] + a_du * dzU[r], mu / (o.kappa_sigma * gap)), o.kappa_sigma * mu / gap);
+        }
+      }
+      evaluate(x, f, c);
+      chdo_grad(h, g.data());
+      eval_jac();
+    }
+    chdo_set_x(h, x.data());
+    if (stats) {
+      stats[0] = f, stats[1] = E0, stats[2] = violu, stats[3] = dual_u, stats[4] = compl_u, stats[5] = mu, stats[6] = delta_w, stats[7] = ls_fail;
+      stats[8] = it, stats[9] = Na, stats[10] = nb, stats[11] = w;
+    }
+    return status;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+// Solves one stage in place (warm start from the problem's current variables).  stats: 12 doubles
+// (f, E0, unscaled violation, unscaled dual inf, unscaled complementarity, mu, delta_w, ls failures, iterations, Na, nb, w).
+int chdo_solve_stage(void* h, int stage, int max_iter, double* stats, int verbose) {
+  Solver S;
+  S.h = h;
+  return S.run(stage, max_iter, stats, verbose);
+}
+}

@@ -64,6 +64,7 @@ def lib():
             ("chdo_lag_hessian", C.c_int, [C.c_void_p, dp, ip, ip, dp]),
             ("chdo_row_times", None, [C.c_void_p, dp]),
             ("chdo_var_times", None, [C.c_void_p, dp, dp]),
+            ("chdo_solve_stage", C.c_int, [C.c_void_p, C.c_int, C.c_int, dp, C.c_int]),
             ("chdo_sample", C.c_int, [C.c_void_p, dp]),
             ("chdo_spline_point", None, [C.c_void_p, C.c_int, C.c_double, dp]),
             ("chdo_spline_num_polys", C.c_int, [C.c_void_p, C.c_int]),
@@ -204,6 +205,33 @@ class OracleProblem:
         t0, t1 = np.zeros(self.n), np.zeros(self.n)
         self.L.chdo_var_times(self.h, _dp(t0), _dp(t1))
         return t0, t1
+
+    def solve_stage(self, stage, max_iter=None, verbose=False):
+        """chd-ipm on the CPU (oracle/ipm_oracle.cpp).  Returns a dict like PhysBatch.solve_stage."""
+        st = STAGES.get(stage, stage)
+        if max_iter is None:
+            max_iter = {0: 7000, 1: 7000, 2: 7000, 3: 2500, 4: 2000, 5: 7000}[st]  # phys_optim.cpp:571,640,652,706,743
+        stats = np.zeros(12)
+        status = self.L.chdo_solve_stage(self.h, st, int(max_iter), _dp(stats), int(verbose))
+        return dict(status=status, iters=int(stats[8]), f=stats[0], E0=stats[1], viol=stats[2], dual=stats[3],
+                    compl=stats[4], mu=stats[5], delta_w=stats[6], ls_fail=int(stats[7]), Na=int(stats[9]),
+                    nb=int(stats[10]), w=int(stats[11]))
+
+    def solve(self):
+        """Staged schedule as the product runs it: 1.1, 1.2 | 2.1, 2.2 | 4 with the three SaveSolution snapshots."""
+        out = {}
+        res = []
+        for st in ("1.1", "1.2"):
+            res.append(self.solve_stage(st))
+        out["no_dynamics"] = self.sample()
+        for st in ("2.1", "2.2"):
+            res.append(self.solve_stage(st))
+        out["dynamics"] = self.sample()
+        res.append(self.solve_stage("4"))
+        out["durations"] = self.sample()
+        out["stages"] = res
+        out["success"] = (res[3]["status"] == 0, res[4]["status"] == 0)
+        return out
 
     def sample(self):
         nf = self.L.chdo_sample(self.h, None)

@@ -64,3 +64,27 @@ def test_solve_schedule_converges(chd):
     n_ee = 2
     flags = s[2, :, :120, 6 + 6 * n_ee:6 + 7 * n_ee]
     assert set(np.unique(flags).tolist()) <= {0.0, 1.0}
+
+
+def test_solved_trajectories_match_cpu_oracle(chd):
+    """Trajectory-level parity: the CUDA solver and the CPU oracle run the same algorithm (chd-ipm); they differ only
+    in floating-point summation order, so iteration counts agree and sampled solutions agree to ~1e-6.
+    Stated tolerance: 1e-5 m / rad-deg on positions and angles, 1e-3 N on forces, contact flags bit-exact."""
+    from oracle.phys import OracleProblem
+    ps = [chd.synth.make_problem(s, n_ee=2) for s in (0, 1)]
+    b = chd.phys.PhysBatch(ps)
+    out = b.solve()
+    for i, p in enumerate(ps):
+        o = OracleProblem(p)
+        ref = o.solve()
+        nf = out["frames"][i]
+        for snap, key in enumerate(["no_dynamics", "dynamics", "durations"]):
+            got = out["samples"][snap, i, :nf]
+            exp = ref[key]
+            assert got.shape == exp.shape
+            np.testing.assert_allclose(got[:, :12], exp[:, :12], rtol=0, atol=1e-5)      # base lin/ang, ee pos
+            np.testing.assert_allclose(got[:, 12:18], exp[:, 12:18], rtol=0, atol=1e-3)  # ee forces
+            np.testing.assert_array_equal(got[:, 18:], exp[:, 18:])                      # contact flags
+        oracle_iters = [s["iters"] for s in ref["stages"]]
+        gpu_iters = [int(out["stage_iters"][s, i]) for s in (0, 1, 2, 3, 5)]
+        assert oracle_iters == gpu_iters, (oracle_iters, gpu_iters)
