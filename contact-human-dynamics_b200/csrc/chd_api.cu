@@ -14,6 +14,8 @@ __global__ void chd_k_stage_begin(ChdDev D, ChdStageDev sg, int max_iter);
 __global__ void chd_k_eval(ChdDev D, ChdStageDev sg, int only_running);
 __global__ void chd_k_init(ChdDev D);
 __global__ void chd_k_kkt(ChdDev D, ChdStageDev sg);
+__global__ void chd_k_kkt_gwin(ChdDev D, ChdStageDev sg);
+__global__ void chd_k_hess_base(ChdDev D, ChdStageDev sg);
 __global__ void chd_k_linesearch(ChdDev D, ChdStageDev sg);
 __global__ void chd_k_sample(ChdDev D, double* out, int* frames_out);
 
@@ -143,17 +145,21 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
 #define AL(field, cnt) if ((rc = dev_alloc(b, (cnt), &D.field))) return rc;
   AL(x, nm) AL(xt, nm) AL(dx, nm) AL(grad, nm) AL(g, mm) AL(gt, mm) AL(Jv, B * hb.slots_max) AL(rflag, mm)
   AL(sc, mm) AL(dL, mm) AL(dU, mm) AL(s, mm) AL(y, mm) AL(zL, mm) AL(zU, mm) AL(ds, mm) AL(dy, mm) AL(dzL, mm) AL(dzU, mm)
-  AL(cost, B * 2) AL(Kband, B * (size_t)hb.Na_max * (hb.w_max + 1)) AL(Kbord, B * (size_t)hb.Na_max * (hb.nb_max + 1))
-  AL(Kcorn, B * (size_t)(hb.nb_max + 1) * (hb.nb_max + 1)) AL(sol, B * (size_t)(hb.Na_max + hb.nb_max)) AL(ipm, B)
+  D.nbc_max = (hb.Na_max + 7) / 8;
+  D.Q = (hb.w_max + 7) / 8 + 1;
+  D.nbt = (hb.nb_max + 1 + 7) / 8;
+  D.win_tiles = std::max(D.Q * (D.Q + 1) / 2, 2 * D.Q);
+  D.kstride = (size_t)D.nbc_max * D.Q * 64 + (size_t)D.nbc_max * D.nbt * 64 + (size_t)64 * D.nbt * D.nbt;
+  AL(cost, B * 2) AL(Kwork, B * D.kstride) AL(Kbase, B * D.kstride) AL(sol, B * (size_t)(hb.Na_max + hb.nb_max)) AL(ipm, B)
 #undef AL
   if ((rc = dev_upload(b, hb.x0, (const double**)&b->d_x0))) return rc;
   CHD_CUDA(cudaMemcpy(D.x, b->d_x0, nm * sizeof(double), cudaMemcpyDeviceToDevice));
   // shared-memory budgets
-  const size_t W = hb.w_max + 1, nbp = hb.nb_max + 1;
+  const size_t nbp8 = 8 * (size_t)D.nbt;
   b->smem_eval = (2 * (size_t)hb.n_max + CHD_THREADS) * sizeof(double);
   b->smem_ls = ((size_t)hb.n_max + CHD_THREADS) * sizeof(double);
-  const size_t kkt_fixed = (CHD_THREADS + (size_t)hb.n_max + nbp * nbp + 2 * (W + nbp)) * sizeof(double);
-  const size_t kkt_win = (W * W + W * nbp) * sizeof(double);
+  const size_t kkt_fixed = (CHD_KKT_THREADS + (size_t)((hb.n_max + 1) & ~1) + 16 * (size_t)D.nbc_max + nbp8 + nbp8 * nbp8 + 2 * (size_t)(D.Q + D.nbt) * 64 + 16) * sizeof(double);
+  const size_t kkt_win = ((size_t)D.win_tiles * 64 + (size_t)D.Q * D.nbt * 64) * sizeof(double);
   int dev = 0, smem_max = 0;
   CHD_CUDA(cudaGetDevice(&dev));
   CHD_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -163,7 +169,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   } else {
     D.win_smem = 0;
     b->smem_kkt = kkt_fixed;
-    if ((rc = dev_alloc(b, B * (W * W + W * nbp), &D.scratch))) return rc;
+    if ((rc = dev_alloc(b, B * (kkt_win / sizeof(double)), &D.scratch))) return rc;
   }
   if (b->smem_eval + 1024 > (size_t)smem_max || b->smem_kkt + 1024 > (size_t)smem_max) {
     fprintf(stderr, "libchd: problem too large for the shared-memory staged kernels (n_max=%d)\n", hb.n_max);
@@ -171,6 +177,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   }
   CHD_CUDA(cudaFuncSetAttribute(chd_k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_eval));
   CHD_CUDA(cudaFuncSetAttribute(chd_k_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_kkt));
+  CHD_CUDA(cudaFuncSetAttribute(chd_k_kkt_gwin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_kkt));
   CHD_CUDA(cudaFuncSetAttribute(chd_k_linesearch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_ls));
   const size_t stride = 6 + 7 * (size_t)hb.n_ee_max;
   CHD_CUDA(cudaMalloc((void**)&b->d_samples, B * hb.fo_max * stride * sizeof(double)));
@@ -276,11 +283,16 @@ int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int
     Timer t(b, KT_INIT);
     chd_k_init<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
   }
+  {
+    Timer t(b, KT_INIT);
+    chd_k_hess_base<<<B, CHD_THREADS, 0, b->stream>>>(b->D, sg);
+  }
   const int check_every = 8;
   for (int it = 0; it <= max_iter; ++it) {
     {
       Timer t(b, KT_KKT);
-      chd_k_kkt<<<B, CHD_THREADS, b->smem_kkt, b->stream>>>(b->D, sg);
+      if (b->D.win_smem) chd_k_kkt<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D, sg);
+      else chd_k_kkt_gwin<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D, sg);
     }
     {
       Timer t(b, KT_LS);
@@ -306,7 +318,8 @@ int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int
       double* s = stats + 8 * i;
       s[0] = I.f, s[1] = I.E0, s[2] = I.viol_u, s[3] = I.dual_u, s[4] = I.compl_u, s[5] = I.mu, s[6] = I.delta_w, s[7] = I.ls_fail;
     }
-    if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "chd prof (Mcycles) seq0 stage %d: err %.2f jasm %.2f hasm %.2f factor %.2f border %.2f back %.2f rec %.2f\n", stage, I.prof[0]/1e6, I.prof[1]/1e6, I.prof[2]/1e6, I.prof[3]/1e6, I.prof[4]/1e6, I.prof[5]/1e6, I.prof[6]/1e6);
+    if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "chd prof (Mcycles) seq0 stage %d: err %.2f jasm %.2f hasm %.2f factor %.2f border %.2f back %.2f rec %.2f | sync-wait after (b) %.2f\n", stage, I.prof[0]/1e6, I.prof[1]/1e6, I.prof[2]/1e6, I.prof[3]/1e6, I.prof[4]/1e6, I.prof[5]/1e6, I.prof[6]/1e6, I.prof[7]/1e6);
+    if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "   worker thread 40: (b) %.2f sync1 %.2f (c) %.2f sync2 %.2f Mcycles\n", I.filt[40]/1e6, I.filt[41]/1e6, I.filt[42]/1e6, I.filt[43]/1e6);
   }
   return 0;
 }

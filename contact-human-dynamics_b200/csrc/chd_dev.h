@@ -5,6 +5,8 @@
 
 #define CHD_FILT_MAX 24
 #define CHD_THREADS 256
+#define CHD_KKT_THREADS 512
+#define CHD_CURV_MIN 1e-8   /* multiplier threshold below which y^+ Jd^T Jd is not added (same in oracle/ipm_oracle.cpp) */
 
 // row flags
 #define CHD_ROW_ACTIVE 1
@@ -30,7 +32,8 @@ struct ChdStageDev {
 
 struct ChdDev {
   int B, S, Pmax, n_max, m_max, slots_max, sets_max, tab_max, F_max, Kd_max, Kr_max, Na_max, nb_max, w_max, par_stride,
-      n_ee_max, fo_max, Ph_max, win_smem;
+      n_ee_max, fo_max, Ph_max, win_smem, nbc_max, Q, nbt, win_tiles;
+  size_t kstride;                             // doubles per sequence of a tile-format KKT buffer (band | bord | corn)
   // ---- static layout ----
   const ChdSeq* seq;
   const double *poly_T, *poly_tend, *node_const, *par, *t_dyn, *t_rom, *t_data, *row_lo, *row_hi;
@@ -45,9 +48,8 @@ struct ChdDev {
   double *sc, *dL, *dU, *s, *y, *zL, *zU, *ds, *dy, *dzL, *dzU;  // B x m_max
   double* cost;                               // B x 2 (current, trial)
   // ---- KKT ----
-  double* Kband;                              // B x Na_max x (w_max+1)   LAPACK lower band, column major
-  double* Kbord;                              // B x Na_max x (nb_max+1)  border rows (+ rhs as the last "row"), column major by band column
-  double* Kcorn;                              // B x (nb_max+1)^2
+  double* Kwork;                              // B x kstride  KKT matrix of the current iteration, overwritten by its factors
+  double* Kbase;                              // B x kstride  per-stage constant part (Gauss-Newton cost Hessian)
   double* sol;                                // B x (Na_max + nb_max)
   double* scratch;                            // elimination window when it does not fit in shared memory
   ChdIpm* ipm;                                // B

@@ -1,0 +1,644 @@
+// KKT kernels of the batched interior-point solver (product code, sm_100a).
+//
+//   chd_k_hess_base : once per stage -- Gauss-Newton Hessian of the (quadratic, fixed-duration) cost terms
+//                     of data_cost.cpp / vel_smooth_cost.cpp, scaled by the objective scaling, in tile format
+//   chd_k_kkt       : per iteration -- IPOPT error measures + barrier update, condensed KKT assembly
+//                     (copy of the base + Jacobian dependent parts), tiled band LDL^T with dense border
+//                     (shared-memory window, FP64 tensor-core trailing updates), triangular solves,
+//                     step recovery and fraction-to-the-boundary rule
+// One CTA per sequence.  Replaces IPOPT's per-iteration MA57 factorisation (phys_optim.cpp:573) for the
+// block-banded systems this NLP produces.
+#include <cuda_runtime.h>
+
+#include "chd_block.cuh"
+#include "chd_eval.cuh"
+#include "chd_kkt_tiles.cuh"
+
+// Gauss-Newton Hessian of a least-squares cost sample: H += wgt * sum_dim J_dim^T J_dim, where the
+// sample is a signed sum over (up to two) located polynomials of B(deriv) node values.
+__device__ void chd_hess_sample(const ChdKT& K, const int* vk, const ChdSpl* P, const double* sign, int np, int deriv, double wgt) {
+  for (int a = 0; a < np * 12; ++a) {
+    const int pa = a / 12, qa = a % 12, va = P[pa].var[qa];
+    if (va < 0) continue;
+    const int ia = vk[va];
+    if (ia < 0) continue;
+    const double wa = sign[pa] * chd_slot_w(P[pa], deriv, qa);
+    if (wa == 0.0) continue;
+    for (int bq = 0; bq < np * 12; ++bq) {
+      const int pb = bq / 12, qb = bq % 12;
+      if ((qb % 3) != (qa % 3)) continue;
+      const int vb = P[pb].var[qb];
+      if (vb < 0) continue;
+      const int ib = vk[vb];
+      if (ib < 0 || ia < ib) continue;
+      const double wb = sign[pb] * chd_slot_w(P[pb], deriv, qb);
+      if (wb != 0.0) chd_kadd(K, ia, ib, wgt * wa * wb);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D, ChdStageDev sg) {
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const ChdSeq* h = D.seq + b;
+  ChdKT K;
+  double* base = D.Kbase + (size_t)b * D.kstride;
+  chd_kt_init(D, h, base, K);
+  for (size_t i = tid; i < D.kstride; i += nt) base[i] = 0.0;
+  __syncthreads();
+  const double sf = D.ipm[b].sf;
+  const int* vk = D.var_kkt + (size_t)b * D.n_max;
+  for (int i = K.Na + tid; i < K.Np; i += nt) K.band[((size_t)(i >> 3) * K.Q) * 64 + (i & 7) * 9] = 1.0;  // identity padding of the band
+  ChdCtx c;
+  chd_make_ctx(D, b, D.x + (size_t)b * D.n_max, c);
+  const int n_ee = h->n_ee, nsp = 2 + n_ee, F = h->F, ns = h->n_smooth;
+  for (int it = tid; it < nsp * F; it += nt) {
+    const int s = it / F, i = it % F, cls = s < 2 ? s : 2;
+    ChdSpl P[2];
+    double sgn[2] = {1.0, -1.0};
+    chd_spl_at(c, s, c.t_data[i], P[1]);
+    if (sg.w_data[cls] != 0.0) chd_hess_sample(K, vk, P + 1, sgn, 1, 0, sf * sg.w_data[cls]);
+    if (i < ns && (sg.w_vel[cls] != 0.0 || sg.w_acc[cls] != 0.0)) {
+      chd_spl_at(c, s, c.t_data[i] + h->dt, P[0]);
+      if (sg.w_vel[cls] != 0.0) chd_hess_sample(K, vk, P, sgn, 2, 0, sf * sg.w_vel[cls]);
+      if (sg.w_acc[cls] != 0.0) chd_hess_sample(K, vk, P, sgn, 2, 1, sf * sg.w_acc[cls]);
+    }
+  }
+}
+
+// dynamic shared memory layout of chd_k_kkt (doubles):
+//   red[CHD_KKT_THREADS] | vecn[n_max] | xs[Np_max + nbp8] | cc[nbp8*nbp8] | ypan[(Q+nbt)*64] | xpan[(Q+nbt)*64] | xs2[Np_max] | dinv[16]
+//   | win[Q(Q+1)/2 * 64] | bwin[Q*nbt*64]            (the last two in global scratch when they do not fit)
+template <bool WS>
+__device__ __forceinline__ void chd_kkt_body(const ChdDev& D, const ChdStageDev& sg) {
+  extern __shared__ double sm[];
+  __shared__ int s_fail;
+  const int b = blockIdx.x;
+  ChdIpm& I = D.ipm[b];
+  if (I.status != 1) return;
+  const ChdSeq* h = D.seq + b;
+  const int n = h->n, m = h->m, tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const size_t ro = (size_t)b * D.m_max, vo = (size_t)b * D.n_max;
+  const int* rf = D.rflag + ro;
+  const int* vk = D.var_kkt + vo;
+  const int* rk = D.row_kkt + ro;
+  const int* ep = D.ent_ptr + (size_t)b * (D.m_max + 1);
+  const int* ec = D.ent_col + (size_t)b * D.slots_max;
+  const double* Jv = D.Jv + (size_t)b * D.slots_max;
+  const double* grad = D.grad + vo;
+  ChdKT K;
+  double* kw = D.Kwork + (size_t)b * D.kstride;
+  chd_kt_init(D, h, kw, K);
+  const int Q = K.Q, nbt = K.nbt, nbp8 = K.nbp8, NBR = K.nbr, nbl = h->nb, nbc = K.nbc;
+  double* red = sm;
+  double* vecn = red + CHD_KKT_THREADS;
+  double* xs = vecn + ((D.n_max + 1) & ~1);   // keep 16-byte alignment for cp.async targets
+  double* cc = xs + (8 * D.nbc_max + nbp8);
+  double* ypan = cc + nbp8 * nbp8;
+  double* xpan = ypan + (Q + nbt) * 64;
+  double* xs2 = xpan + (Q + nbt) * 64;
+  double* dinv = xs2 + 8 * D.nbc_max;
+  double* win = WS ? dinv + 16 : D.scratch + (size_t)b * ((size_t)D.win_tiles * 64 + (size_t)Q * nbt * 64);
+  double* bwin = win + (size_t)D.win_tiles * 64;
+  const double sf = I.sf;
+  double mu = I.mu;
+  long long tk0 = clock64();
+#define CHD_PROF(slot) do { __syncthreads(); if (tid == 0) { long long t_ = clock64(); I.prof[slot] += (double)(t_ - tk0); tk0 = t_; } } while (0)
+
+  // ---------------- A. error measures, convergence, barrier update ----------------
+  for (int i = tid; i < n; i += nt) vecn[i] = sf * grad[i];
+  __syncthreads();
+  double a_ysum = 0, a_zsum = 0, a_cviol = 0, a_theta = 0, a_rs = 0, a_cmax = -INFINITY, a_cmin = INFINITY, a_violu = 0;
+  for (int r = tid; r < m; r += nt) {
+    const int f = rf[r];
+    if (!(f & CHD_ROW_ACTIVE)) continue;
+    const double sc = D.sc[ro + r], gval = D.g[ro + r], d = sc * gval, y = D.y[ro + r];
+    a_ysum += fabs(y);
+    a_violu = fmax(a_violu, fmax(D.row_lo[ro + r] - gval, gval - D.row_hi[ro + r]));
+    const double ys = sc * y;
+    if (ys != 0.0)
+      for (int e = ep[r]; e < ep[r + 1]; ++e) {
+        const int col = ec[e];
+        if (col >= 0) atomicAdd(vecn + col, ys * Jv[e]);
+      }
+    if (f & CHD_ROW_EQ) {
+      const double re = d - D.dL[ro + r];
+      a_cviol = fmax(a_cviol, fabs(re));
+      a_theta += fabs(re);
+    } else {
+      const double s = D.s[ro + r], ri = d - s, zL = D.zL[ro + r], zU = D.zU[ro + r];
+      a_cviol = fmax(a_cviol, fabs(ri));
+      a_theta += fabs(ri);
+      a_rs = fmax(a_rs, fabs(-y - zL + zU));
+      a_zsum += zL + zU;
+      if (f & CHD_ROW_HASL) { const double cp = (s - D.dL[ro + r]) * zL; a_cmax = fmax(a_cmax, cp); a_cmin = fmin(a_cmin, cp); }
+      if (f & CHD_ROW_HASU) { const double cp = (D.dU[ro + r] - s) * zU; a_cmax = fmax(a_cmax, cp); a_cmin = fmin(a_cmin, cp); }
+    }
+  }
+  __syncthreads();
+  double a_dual = 0;
+  for (int i = tid; i < n; i += nt)
+    if (vk[i] >= 0) a_dual = fmax(a_dual, fabs(vecn[i]));
+  const double ysum = chd_block_sum(a_ysum, red), zsum = chd_block_sum(a_zsum, red);
+  const double cviol = chd_block_max(a_cviol, red), theta = chd_block_sum(a_theta, red);
+  const double dual_inf = fmax(chd_block_max(a_dual, red), chd_block_max(a_rs, red));
+  const double cmax = chd_block_max(a_cmax, red), cmin = chd_block_min(a_cmin, red);
+  const double violu = fmax(chd_block_max(a_violu, red), 0.0);
+  const int nbnd = I.n_bounds;
+  const double s_d = fmax(CHD_S_MAX, (ysum + zsum) / fmax((double)(I.m_act + nbnd), 1.0)) / CHD_S_MAX;
+  const double s_c = fmax(CHD_S_MAX, zsum / fmax((double)nbnd, 1.0)) / CHD_S_MAX;
+  auto compl_err = [&](double mm) { return nbnd > 0 ? fmax(fabs(cmax - mm), fabs(cmin - mm)) : 0.0; };
+  const double E0 = fmax(fmax(dual_inf / s_d, cviol), compl_err(0.0) / s_c);
+  const double dual_u = dual_inf / sf, compl_u = compl_err(0.0) / sf;
+  bool done = false;
+  int new_status = 1;
+  if (E0 <= CHD_TOL && violu <= CHD_CONSTR_VIOL_TOL && dual_u <= CHD_DUAL_INF_TOL && compl_u <= CHD_COMPL_INF_TOL) new_status = 0, done = true;
+  else if (I.iter >= I.max_iter) new_status = -1, done = true;
+  if (!done) {
+    const double mu_min = fmin(CHD_TOL, CHD_COMPL_INF_TOL) / (CHD_KAPPA_EPS + 1.0);
+    while (true) {
+      const double Emu = fmax(fmax(dual_inf / s_d, cviol), compl_err(mu) / s_c);
+      if (Emu <= CHD_KAPPA_EPS * mu && mu > mu_min) mu = fmax(mu_min, fmin(CHD_KAPPA_MU * mu, pow(mu, CHD_THETA_MU)));
+      else break;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    I.f = D.cost[2 * b];
+    I.E0 = E0, I.viol_u = violu, I.dual_u = dual_u, I.compl_u = compl_u;
+    I.status = new_status;
+    s_fail = 0;
+    if (!done) {
+      I.mu = mu;
+      I.tau = fmax(CHD_TAU_MIN, 1.0 - mu);
+      if (I.iter == 0) I.theta_max = 1e4 * fmax(1.0, theta), I.theta_min = 1e-4 * fmax(1.0, theta);
+      if (mu != I.mu_filter) I.nfilt = 0, I.mu_filter = mu;
+      I.theta0 = theta;
+    }
+  }
+  if (done) return;
+  const double tau = fmax(CHD_TAU_MIN, 1.0 - mu);
+  const double delta_w = I.delta_w;
+  CHD_PROF(0);
+
+  // ---------------- B. assemble the KKT system ----------------
+  // Narrow inequality rows (<= 12 slots: terrain, friction pyramid, height) are condensed into the primal block
+  // (J^T Sigma J); wide ones (leg length) keep their multiplier as an unknown with diagonal
+  // -1/Sigma, which needs 36 instead of 666 matrix updates per row.  The right-hand side is accumulated in
+  // shared memory (xs) and written out once.
+  {
+    const double* base = D.Kbase + (size_t)b * D.kstride;
+    const double2* src = reinterpret_cast<const double2*>(base);
+    double2* dst = reinterpret_cast<double2*>(kw);
+    const size_t cnt2 = D.kstride / 2;
+    size_t i = tid;
+    for (; i + 3 * (size_t)nt < cnt2; i += 4 * (size_t)nt) {   // four independent 16-byte loads in flight per thread
+      const double2 v0 = src[i], v1 = src[i + nt], v2 = src[i + 2 * (size_t)nt], v3 = src[i + 3 * (size_t)nt];
+      dst[i] = v0, dst[i + nt] = v1, dst[i + 2 * (size_t)nt] = v2, dst[i + 3 * (size_t)nt] = v3;
+    }
+    for (; i < cnt2; i += nt) dst[i] = src[i];
+  }
+  const int Na = K.Na;
+  double* rhs_s = xs;   // [0, Np) band unknowns, [8*nbc_max, +nb) border unknowns
+  for (int i = tid; i < 8 * D.nbc_max + nbp8; i += nt) rhs_s[i] = 0.0;
+  __syncthreads();
+  auto rhs_add = [&](int kk, double v) { atomicAdd(rhs_s + (kk < Na ? kk : 8 * D.nbc_max + (kk - Na)), v); };
+  for (int i = tid; i < n; i += nt) {
+    const int k = vk[i];
+    if (k < 0) continue;
+    chd_kadd(K, k, k, delta_w);
+    rhs_add(k, -sf * grad[i]);
+  }
+  for (int r = tid; r < m; r += nt) {
+    const int f = rf[r];
+    const int k = rk[r];
+    if (!(f & CHD_ROW_ACTIVE)) {
+      if (k >= 0) chd_kadd(K, k, k, -1.0);   // row of an inactive set: decoupled dummy unknown
+      continue;
+    }
+    const double sc = D.sc[ro + r];
+    const int e0 = ep[r], e1 = ep[r + 1];
+    if (k >= 0) {
+      // explicit row: equality, or wide inequality with its slack eliminated
+      double diag = -CHD_DELTA_C, rr;
+      if (f & CHD_ROW_EQ) {
+        rr = -(sc * D.g[ro + r] - D.dL[ro + r]);
+      } else {
+        const double s = D.s[ro + r];
+        const double gapL = (f & CHD_ROW_HASL) ? s - D.dL[ro + r] : 1.0, gapU = (f & CHD_ROW_HASU) ? D.dU[ro + r] - s : 1.0;
+        const double Sig = ((f & CHD_ROW_HASL) ? D.zL[ro + r] / gapL : 0.0) + ((f & CHD_ROW_HASU) ? D.zU[ro + r] / gapU : 0.0);
+        const double bvec = ((f & CHD_ROW_HASL) ? mu / gapL : 0.0) - ((f & CHD_ROW_HASU) ? mu / gapU : 0.0);
+        diag -= 1.0 / Sig;
+        rr = -(sc * D.g[ro + r] - s) + (D.y[ro + r] + bvec) / Sig;
+      }
+      chd_kadd(K, k, k, diag);
+      rhs_add(k, rr);
+      const double ys = sc * D.y[ro + r];
+      for (int e = e0; e < e1; ++e) {
+        const int col = ec[e];
+        if (col < 0) continue;
+        const int kc = vk[col];
+        if (kc < 0) continue;
+        const double jv = Jv[e];
+        if (jv == 0.0) continue;
+        chd_kadd(K, k, kc, sc * jv);
+        rhs_add(kc, -ys * jv);
+      }
+    } else {
+      // condensed narrow inequality row
+      const double s = D.s[ro + r];
+      const double gapL = (f & CHD_ROW_HASL) ? s - D.dL[ro + r] : 1.0, gapU = (f & CHD_ROW_HASU) ? D.dU[ro + r] - s : 1.0;
+      const double Sig = ((f & CHD_ROW_HASL) ? D.zL[ro + r] / gapL : 0.0) + ((f & CHD_ROW_HASU) ? D.zU[ro + r] / gapU : 0.0);
+      const double bvec = ((f & CHD_ROW_HASL) ? mu / gapL : 0.0) - ((f & CHD_ROW_HASU) ? mu / gapU : 0.0);
+      const double coef = Sig * (sc * D.g[ro + r] - s) - bvec;
+      for (int ea = e0; ea < e1; ++ea) {
+        const int ca = ec[ea];
+        if (ca < 0) continue;
+        const int ka = vk[ca];
+        if (ka < 0) continue;
+        const double va = sc * Jv[ea];
+        if (va == 0.0) continue;
+        rhs_add(ka, -va * coef);
+        for (int eb = e0; eb < e1; ++eb) {
+          const int cb = ec[eb];
+          if (cb < 0) continue;
+          const int kb = vk[cb];
+          if (kb < 0 || ka < kb) continue;
+          const double vb = sc * Jv[eb];
+          if (vb != 0.0) chd_kadd(K, ka, kb, Sig * va * vb);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < K.Np; i += nt) K.bord[((size_t)(i >> 3) * nbt + (NBR >> 3)) * 64 + (NBR & 7) * 8 + (i & 7)] = i < Na ? rhs_s[i] : 0.0;
+  for (int i = tid; i < nbl; i += nt) K.corn[(size_t)NBR * nbp8 + i] = rhs_s[8 * D.nbc_max + i];
+  CHD_PROF(1);
+  // y^+ * Jd^T Jd of the squared-distance rows (leg length, toe-heel distance): one warp per active row.
+  // per-warp scratch (in the not yet used window memory): slot -> (kkt index, weight, 3-vector column of Jd)
+  {
+    ChdCtx c;
+    chd_make_ctx(D, b, D.x + vo, c);
+    double* ws = win + warp * 192;
+    for (int si = 0; si < h->nsets; ++si) {
+      const ChdSet st = c.sets[si];
+      if (!(sg.set_mask & CHD_MASK(st.type))) continue;
+      if (st.type != CHD_SET_ROM && st.type != CHD_SET_HEEL) continue;
+      const int nslot = st.type == CHD_SET_ROM ? 36 : 24;
+      for (int k = warp; k < st.nitems; k += nwarp) {
+        const int R = st.row0 + k;
+        const double yc = D.sc[ro + R] * D.y[ro + R];
+        if (!(yc > CHD_CURV_MIN)) continue;
+        const double t = c.t_rom[k];
+        ChdSpl P0, P1, P2;
+        double dRh[3][3];
+        if (st.type == CHD_SET_ROM) {
+          // d = p_ee - R(e) h - c : blocks lin (-B e_dim), ang (-B dR_dim h), ee (+B e_dim)
+          chd_spl_at(c, 0, t, P0);
+          chd_spl_at(c, 1, t, P1);
+          chd_spl_at(c, chd_sp_motion(st.a), t, P2);
+          double e[3];
+          chd_spl_val(c, P1, 0, e);
+          ChdTrig tr;
+          chd_trig(e, tr);
+          const double* hip = chd_hip(c, st.a, t);
+          for (int j = 0; j < 3; ++j) {
+            double Dj[9];
+            chd_dR(tr, j, Dj);
+            chd_mv(Dj, hip, dRh[j]);
+          }
+        } else {
+          chd_spl_at(c, chd_sp_motion(st.a), t, P0);   // d = p_a - p_b
+          chd_spl_at(c, chd_sp_motion(st.b), t, P1);
+        }
+        for (int a = lane; a < nslot; a += 32) {
+          const int ba = a / 12, qa = a % 12, da = qa % 3;
+          const ChdSpl& Pa = ba == 0 ? P0 : (ba == 1 ? P1 : P2);
+          const int va = Pa.var[qa];
+          const int ia = va >= 0 ? vk[va] : -1;
+          double sgn, v3[3] = {da == 0 ? 1.0 : 0.0, da == 1 ? 1.0 : 0.0, da == 2 ? 1.0 : 0.0};
+          if (st.type == CHD_SET_ROM) {
+            sgn = ba == 2 ? 1.0 : -1.0;
+            if (ba == 1) v3[0] = dRh[da][0], v3[1] = dRh[da][1], v3[2] = dRh[da][2];
+          } else {
+            sgn = ba == 0 ? 1.0 : -1.0;
+          }
+          ws[a * 5 + 0] = (double)ia;
+          ws[a * 5 + 1] = ia >= 0 ? sgn * chd_slot_w(Pa, 0, qa) : 0.0;
+          ws[a * 5 + 2] = v3[0], ws[a * 5 + 3] = v3[1], ws[a * 5 + 4] = v3[2];
+        }
+        __syncwarp();
+        for (int idx = lane; idx < nslot * nslot; idx += 32) {
+          const int a = idx / nslot, bq = idx - a * nslot;
+          const double wa = ws[a * 5 + 1], wb = ws[bq * 5 + 1];
+          if (wa == 0.0 || wb == 0.0) continue;
+          const int ia = (int)ws[a * 5], ib = (int)ws[bq * 5];
+          if (ia < ib) continue;
+          const double dotv = ws[a * 5 + 2] * ws[bq * 5 + 2] + ws[a * 5 + 3] * ws[bq * 5 + 3] + ws[a * 5 + 4] * ws[bq * 5 + 4];
+          if (dotv != 0.0) chd_kadd(K, ia, ib, yc * wa * wb * dotv);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  CHD_PROF(2);
+
+  // ---------------- C. tiled band LDL^T with dense border ----------------
+  // corner (incl. rhs row) to shared memory; initial window: band tiles (I, J), 0 <= J <= I <= q and border columns 0..q
+  for (int i = tid; i < nbp8 * nbp8; i += nt) cc[i] = K.corn[i];
+  for (int idx = tid; idx < Q * Q * 64; idx += nt) {
+    const int e = idx & 63, pr = idx >> 6, J = pr / Q, t = pr % Q;
+    if (J + t < Q && J < nbc && J + t < nbc) win[chd_win_slot(J + t, J, Q) * 64 + e] = K.band[((size_t)J * Q + t) * 64 + e];
+  }
+  for (int idx = tid; idx < Q * nbt * 64; idx += nt) {
+    const int J = idx / (nbt * 64);
+    if (J < nbc) bwin[idx] = K.bord[(size_t)J * nbt * 64 + idx % (nbt * 64)];
+  }
+  __syncthreads();
+  // index tables: pair list (gi >= gj) over band groups 0..q-1 and border groups q..q+nbt-1 (built once),
+  // window slot of every band group of the current block column (double buffered, no integer division)
+  __shared__ int s_rs[2][96];
+  __shared__ int s_gnz[2][96];   // per panel group: any non-zero entry in the X tile (zero tiles skip their trailing updates)
+  __shared__ unsigned short s_pairs[3000];
+  const int GB = K.q, Gm = K.q + nbt, npairs = Gm * (Gm + 1) / 2;
+  for (int p = tid; p < npairs && p < 3000; p += nt) {
+    int gi = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while (gi * (gi + 1) / 2 > p) --gi;
+    while ((gi + 1) * (gi + 2) / 2 <= p) ++gi;
+    s_pairs[p] = (unsigned short)((gi << 8) | (p - gi * (gi + 1) / 2));
+  }
+  auto tri = [](int a_, int b_) { return a_ > b_ ? a_ * (a_ + 1) / 2 + b_ : b_ * (b_ + 1) / 2 + a_; };
+  for (int g = tid; g < GB; g += nt) s_rs[0][g] = (1 + g) % Q;
+  for (int g = tid; g < 96; g += nt) s_gnz[0][g] = 0, s_gnz[1][g] = 0;
+  if (warp == 0) {
+    const bool ok = chd_tile_ldl(win, dinv, lane);   // tile (0,0) sits in slot 0
+    if (!ok && lane == 0) s_fail = 1;
+  }
+  __syncthreads();
+  int kslot = 0, cur = 0;  // kslot = Kc % Q
+  for (int Kc = 0; Kc < nbc; ++Kc, cur ^= 1) {
+    const int tq = min(K.q, nbc - 1 - Kc);          // band tiles below the diagonal tile
+    const int* rs = s_rs[cur];
+    double* Tkk = win + (size_t)tri(kslot, kslot) * 64;
+    double* Bk = bwin + (size_t)kslot * nbt * 64;
+    const double* dv = dinv + 8 * cur;
+    // (b) panel rows: x = a L0^-T D^-1 -> xpan + global (final L), y = a L0^-T -> ypan; diag tile -> global
+    for (int row = tid; row < 8 * tq + nbp8; row += nt) {
+      const bool band_row = row < 8 * tq;
+      const int prow = band_row ? row : 8 * GB + row - 8 * tq;       // row id inside the panel buffers
+      const double* src = band_row ? win + (size_t)tri(rs[row >> 3], kslot) * 64 + (row & 7) * 8 : Bk + (row - 8 * tq) * 8;
+      double a8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a8[c] = src[c];
+      chd_row_trsm(a8, Tkk, dv, ypan + prow * 8);
+      double* gdst = band_row ? K.band + ((size_t)Kc * Q + 1) * 64 + row * 8 : K.bord + (size_t)Kc * nbt * 64 + (row - 8 * tq) * 8;
+      bool nzr = false;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) xpan[prow * 8 + c] = a8[c], gdst[c] = a8[c], nzr = nzr || a8[c] != 0.0;
+      if (nzr) s_gnz[cur][prow >> 3] = 1;
+    }
+    for (int e = tid; e < 64; e += nt) K.band[(size_t)Kc * Q * 64 + e] = Tkk[e];
+    __syncthreads();
+    // (c) stream in block row Kc + Q (its slots are dead now), trailing updates on the fp64 tensor core;
+    //     warp 0 takes the pair that completes the next diagonal tile and factors it right away
+    const int In = Kc + Q;
+    if (In < nbc) {
+      for (int idx = tid; idx < Q * 32 + nbt * 32; idx += nt) {   // 16-byte chunks
+        const int tile = idx >> 5, off = (idx & 31) * 2;
+        if (tile < Q) {
+          const int J = tile < GB ? Kc + 1 + tile : In;
+          double* dst = tile < GB ? win + (size_t)tri(kslot, rs[tile]) * 64 : Tkk;
+          chd_copy16(dst + off, K.band + ((size_t)J * Q + (In - J)) * 64 + off, WS);
+        } else {
+          chd_copy16(Bk + (tile - Q) * 64 + off, K.bord + (size_t)In * nbt * 64 + (tile - Q) * 64 + off, WS);
+        }
+      }
+    }
+    if (warp == 0) {
+      if (tq >= 1) {
+        double* Tn = win + (size_t)tri(rs[0], rs[0]) * 64;
+        long long tb0 = clock64();
+        chd_tile_sub_xyT(Tn, xpan, ypan, lane);
+        __syncwarp();
+        const bool ok = chd_tile_ldl(Tn, dinv + 8 * (cur ^ 1), lane);
+        if (lane == 0) I.prof[7] += (double)(clock64() - tb0);
+        if (!ok && lane == 0) s_fail = 1;
+      }
+    } else {
+      if (warp == 1) {
+        for (int g = lane; g < GB; g += 32) {   // slot table of the next block column
+          int v = kslot + 2 + g;
+          while (v >= Q) v -= Q;
+          s_rs[cur ^ 1][g] = v;
+        }
+        for (int g = lane; g < Gm; g += 32) s_gnz[cur ^ 1][g] = 0;
+      }
+      // compact list of the groups with a non-zero X tile (every warp builds it redundantly: no extra barrier).
+      // the pair table enumerates (i >= j) row by row, so its first na(na+1)/2 entries pair the first na entries.
+      const int* gnz = s_gnz[cur];
+      int myg = -1, na;
+      {
+        const bool act = lane < Gm && (lane >= GB || lane < tq) && gnz[lane];
+        const unsigned msk = __ballot_sync(0xffffffffu, act);
+        na = __popc(msk);
+        // lane l receives the id of the l-th active group
+        const unsigned sel = __fns(msk, 0, lane + 1);   // position of the (lane+1)-th set bit
+        myg = lane < na ? (int)sel : -1;
+      }
+      const bool compact = Gm <= 32;
+      const int np_loop = compact ? na * (na + 1) / 2 : npairs;
+      for (int p = warp - 1; p < np_loop; p += nwarp - 1) {
+        const int ai = s_pairs[p] >> 8, aj = s_pairs[p] & 255;
+        int gi, gj;
+        if (compact) {
+          gi = __shfl_sync(0xffffffffu, myg, ai), gj = __shfl_sync(0xffffffffu, myg, aj);
+        } else {
+          gi = ai, gj = aj;
+          if ((gi < GB && gi >= tq) || (gj < GB && gj >= tq) || !gnz[gi] || !gnz[gj]) continue;
+        }
+        if (gi == 0 && gj == 0) continue;   // the next diagonal tile is updated by warp 0
+        const double* X = xpan + gi * 64;
+        const double* Y = ypan + gj * 64;
+        if (gi < GB) {
+          chd_tile_sub_xyT(win + (size_t)tri(rs[gi], rs[gj]) * 64, X, Y, lane);
+        } else if (gj < GB) {
+          chd_tile_sub_xyT(bwin + ((size_t)rs[gj] * nbt + (gi - GB)) * 64, X, Y, lane);
+        } else {
+          const int bi = gi - GB, bj = gj - GB;  // corner block: strided rows, scalar code
+          for (int e = lane; e < 64; e += 32) {
+            const int r = e >> 3, cq = e & 7;
+            double acc = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) acc += X[r * 8 + kk] * Y[cq * 8 + kk];
+            cc[(bi * 8 + r) * nbp8 + bj * 8 + cq] -= acc;
+          }
+        }
+      }
+    }
+    chd_copy_wait(WS);
+    __syncthreads();
+    kslot = kslot + 1 == Q ? 0 : kslot + 1;
+  }
+  CHD_PROF(3);
+  // dense LDL^T of the border Schur complement S = cc[0..nbl)^2 and solve S xb = rb (rb = row NBR of cc)
+  for (int k = 0; k < nbl; ++k) {
+    const double dk = cc[k * nbp8 + k];
+    if (tid == 0 && !(dk > 0.0 && isfinite(dk))) s_fail = 1;
+    __syncthreads();
+    const double ik = 1.0 / dk;
+    const int rem = nbl - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+      if (j <= i) cc[i * nbp8 + j] -= cc[i * nbp8 + k] * ik * cc[j * nbp8 + k];
+    }
+    for (int j = k + 1 + tid; j < nbl; j += nt) cc[NBR * nbp8 + j] -= cc[j * nbp8 + k] * ik * cc[NBR * nbp8 + k];
+    __syncthreads();
+  }
+  double* xb = xs + 8 * D.nbc_max;  // border solution
+  if (tid == 0) {
+    for (int k = nbl - 1; k >= 0; --k) {
+      double v = cc[NBR * nbp8 + k] / cc[k * nbp8 + k];
+      for (int i = k + 1; i < nbl; ++i) v -= (cc[i * nbp8 + k] / cc[k * nbp8 + k]) * xb[i];
+      xb[k] = v;
+    }
+  }
+  __syncthreads();
+  double* sol = D.sol + (size_t)b * (D.Na_max + D.nb_max);
+  for (int i = tid; i < nbl; i += nt) sol[Na + i] = xb[i];
+  CHD_PROF(4);
+  // backward substitution, column oriented: acc = u - Lb^T xb; for K descending: x_K = L0^-T acc_K (warp 0),
+  // then acc_J -= L(K,J)^T x_K for the block row K (all threads).  Tiles are staged two block rows ahead.
+  {
+    double* accv = xpan;                  // panel buffers are free now; accv needs 8*nbc doubles <= (Q+nbt)*64? no -> use xs2
+    accv = xs2;
+    for (int i = tid; i < K.Np; i += nt) {
+      const double* bt = K.bord + (size_t)(i >> 3) * nbt * 64 + (i & 7);
+      double v = bt[NBR * 8];
+      for (int q2 = 0; q2 < nbl; ++q2) v -= bt[q2 * 8] * xb[q2];
+      accv[i] = v;
+    }
+    // staging buffers in the (now free) window: stg[buf] = diag tile | tiles (K, K-1-g), g = 0..q-1
+    const int per = Q * 64;
+    double* stg = win;
+    auto stage_row = [&](int Kr, int buf) {
+      if (Kr < 0) return;
+      for (int idx = tid; idx < Q * 32; idx += nt) {
+        const int tile = idx >> 5, off = (idx & 31) * 2;
+        const int J = tile == 0 ? Kr : Kr - tile;     // tile 0: diagonal; tile g+1: (Kr, Kr-1-g)
+        if (J < 0) continue;
+        chd_copy16(stg + (size_t)buf * per + tile * 64 + off, K.band + ((size_t)J * Q + (Kr - J)) * 64 + off, WS);
+      }
+    };
+    stage_row(nbc - 1, 0);
+    chd_copy_wait(WS);
+    __syncthreads();
+    int buf = 0;
+    for (int Kc = nbc - 1; Kc >= 0; --Kc, buf ^= 1) {
+      const double* T0 = stg + (size_t)buf * per;
+      stage_row(Kc - 1, buf ^ 1);
+      if (warp == 0) {
+        double xk[8];
+#pragma unroll
+        for (int c = 7; c >= 0; --c) {
+          double v = accv[Kc * 8 + c];
+#pragma unroll
+          for (int p = c + 1; p < 8; ++p) v -= T0[p * 8 + c] * xk[p];
+          xk[c] = v;
+        }
+        if (lane < 8) {
+          const int gi = Kc * 8 + lane;
+          double v = xk[0];
+#pragma unroll
+          for (int c = 1; c < 8; ++c) v = lane == c ? xk[c] : v;
+          xs[gi] = v;
+          if (gi < Na) sol[gi] = v;
+        }
+      }
+      __syncthreads();
+      const int nrow = min(K.q, Kc);   // tiles (Kc, Kc-1-g), g < nrow
+      for (int idx = tid; idx < nrow * 8; idx += nt) {
+        const int g = idx >> 3, c = idx & 7;
+        const double* T = T0 + (g + 1) * 64;
+        double v = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v += T[r * 8 + c] * xs[Kc * 8 + r];
+        accv[(Kc - 1 - g) * 8 + c] -= v;
+      }
+      chd_copy_wait(WS);
+      __syncthreads();
+    }
+  }
+  CHD_PROF(5);
+  if (s_fail) {
+    // numerical breakdown: raise the primal regularisation and retry next iteration (no step is taken)
+    if (tid == 0) {
+      I.delta_w = fmin(fmax(I.delta_w * 100.0, 1e-4), CHD_DW_MAX * 10);
+      I.a_pr = 0.0, I.a_du = 0.0, I.dphi = 0.0;
+      I.ls_fail += 1;
+      if (I.delta_w > CHD_DW_MAX) I.status = -2;
+    }
+    for (int i = tid; i < n; i += nt) D.dx[vo + i] = 0.0;
+    for (int r = tid; r < m; r += nt) D.ds[ro + r] = 0.0, D.dy[ro + r] = 0.0, D.dzL[ro + r] = 0.0, D.dzU[ro + r] = 0.0;
+    return;
+  }
+  __syncthreads();
+
+  // ---------------- D. recover the full step, fraction-to-the-boundary, line-search inputs ----------------
+  double* dx = D.dx + vo;
+  for (int i = tid; i < n; i += nt) {
+    const int k = vk[i];
+    const double v = k >= 0 ? sol[k] : 0.0;
+    dx[i] = v;
+    vecn[i] = v;
+  }
+  __syncthreads();
+  double a_pr = 1.0, a_du = 1.0, a_dphi = 0.0, a_phi = 0.0;
+  for (int i = tid; i < n; i += nt) a_dphi += sf * grad[i] * vecn[i];
+  for (int r = tid; r < m; r += nt) {
+    const int f = rf[r];
+    if (!(f & CHD_ROW_ACTIVE)) continue;
+    if (f & CHD_ROW_EQ) {
+      D.dy[ro + r] = sol[rk[r]];
+      D.ds[ro + r] = 0.0;
+      continue;
+    }
+    const double sc = D.sc[ro + r], s = D.s[ro + r];
+    double Jdx = 0.0;
+    for (int e = ep[r]; e < ep[r + 1]; ++e) {
+      const int col = ec[e];
+      if (col >= 0) Jdx += Jv[e] * vecn[col];
+    }
+    const double riq = sc * D.g[ro + r] - s;
+    const double ds = sc * Jdx + riq;
+    const bool hl = f & CHD_ROW_HASL, hu = f & CHD_ROW_HASU;
+    const double gapL = hl ? s - D.dL[ro + r] : 1.0, gapU = hu ? D.dU[ro + r] - s : 1.0;
+    const double zL = D.zL[ro + r], zU = D.zU[ro + r];
+    const double sigL = hl ? zL / gapL : 0.0, sigU = hu ? zU / gapU : 0.0;
+    const double bvec = (hl ? mu / gapL : 0.0) - (hu ? mu / gapU : 0.0);
+    const double dy = (sigL + sigU) * ds - D.y[ro + r] - bvec;
+    const double dzL = hl ? mu / gapL - zL - sigL * ds : 0.0;
+    const double dzU = hu ? mu / gapU - zU + sigU * ds : 0.0;
+    D.ds[ro + r] = ds, D.dy[ro + r] = dy, D.dzL[ro + r] = dzL, D.dzU[ro + r] = dzU;
+    if (hl && ds < 0) a_pr = fmin(a_pr, -tau * gapL / ds);
+    if (hu && ds > 0) a_pr = fmin(a_pr, tau * gapU / ds);
+    if (hl && dzL < 0) a_du = fmin(a_du, -tau * zL / dzL);
+    if (hu && dzU < 0) a_du = fmin(a_du, -tau * zU / dzU);
+    if (hl) a_dphi -= mu * ds / gapL, a_phi -= mu * log(gapL);
+    if (hu) a_dphi += mu * ds / gapU, a_phi -= mu * log(gapU);
+  }
+  a_pr = chd_block_min(a_pr, red);
+  a_du = chd_block_min(a_du, red);
+  const double dphi = chd_block_sum(a_dphi, red);
+  const double phib = chd_block_sum(a_phi, red);
+  if (tid == 0) {
+    I.a_pr = a_pr, I.a_du = a_du, I.dphi = dphi;
+    I.phi0 = sf * D.cost[2 * b] + phib;
+  }
+  CHD_PROF(6);
+}
+
+// the elimination window lives in shared memory (WS) or, for very wide bands, in a global scratch buffer
+__global__ void __launch_bounds__(CHD_KKT_THREADS) chd_k_kkt(ChdDev D, ChdStageDev sg) { chd_kkt_body<true>(D, sg); }
+__global__ void __launch_bounds__(CHD_KKT_THREADS) chd_k_kkt_gwin(ChdDev D, ChdStageDev sg) { chd_kkt_body<false>(D, sg); }

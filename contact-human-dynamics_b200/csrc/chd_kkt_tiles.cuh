@@ -1,0 +1,139 @@
+// Tiled (8x8) symmetric arrowhead storage of the condensed KKT matrix and its factorisation primitives
+// (product code, device only).
+//
+//   [ A  B^T ]   A : banded, order Np (= Na padded to a multiple of 8 with identity), half bandwidth <= 8*q
+//   [ B  C   ]   B : dense border rows (long-lived stance-position variables) + the right-hand side as one more row
+//
+// Global layout per sequence (doubles):  band | bord | corn
+//   band : block column J (8 columns) holds Q = q+1 tiles (I = J .. J+q), tile = 8x8 row major
+//   bord : block column J holds nbt tiles of border rows (row b -> tile b>>3, r = b&7)
+//   corn : nbp8 x nbp8 dense, row major (nbp8 = 8*nbt); row `nbr` carries the border part of the rhs
+// The factorisation is an unpivoted block LDL^T (the matrix is quasi-definite by construction):
+// per block column: 8x8 diagonal LDL^T (warp shuffles), row-wise triangular solves of the panel, and
+// FP64 tensor-core (mma.sync m8n8k4) rank-8 trailing updates of the shared-memory window.
+#pragma once
+#include "chd_dev.h"
+
+struct ChdKT {
+  int Na, Np, nbc, q, Q, nbt, nbp8, nbr;
+  double *band, *bord, *corn;
+};
+
+__device__ __forceinline__ void chd_kt_init(const ChdDev& D, const ChdSeq* h, double* base, ChdKT& K) {
+  K.Na = h->Na;
+  K.Np = (h->Na + 7) & ~7;
+  K.nbc = K.Np >> 3;
+  K.Q = D.Q;
+  K.q = D.Q - 1;
+  K.nbt = D.nbt;
+  K.nbp8 = 8 * D.nbt;
+  K.nbr = D.nb_max;
+  K.band = base;
+  K.bord = base + (size_t)D.nbc_max * D.Q * 64;
+  K.corn = K.bord + (size_t)D.nbc_max * D.nbt * 64;
+}
+
+// add v at position (i, j) of the symmetric matrix (lower triangle storage); unknown index >= Na = border
+__device__ __forceinline__ void chd_kadd(const ChdKT& K, int i, int j, double v) {
+  if (i < j) { int t = i; i = j; j = t; }
+  if (i < K.Na) {
+    const int J = j >> 3;
+    atomicAdd(K.band + ((size_t)J * K.Q + ((i >> 3) - J)) * 64 + (i & 7) * 8 + (j & 7), v);
+  } else if (j < K.Na) {
+    const int b = i - K.Na;
+    atomicAdd(K.bord + ((size_t)(j >> 3) * K.nbt + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7), v);
+  } else {
+    atomicAdd(K.corn + (size_t)(i - K.Na) * K.nbp8 + (j - K.Na), v);
+  }
+}
+__device__ __forceinline__ void chd_radd(const ChdKT& K, int i, double v) {  // right-hand side
+  if (i < K.Na) atomicAdd(K.bord + ((size_t)(i >> 3) * K.nbt + (K.nbr >> 3)) * 64 + (K.nbr & 7) * 8 + (i & 7), v);
+  else atomicAdd(K.corn + (size_t)K.nbr * K.nbp8 + (i - K.Na), v);
+}
+
+// D(8x8) = C - X * Y^T for row-major 8x8 tiles X, Y (fp64 tensor core, two k-steps of m8n8k4).
+// Fragment layout (PTX ISA, mma.m8n8k4 f64): A[row = lane>>2][k = lane&3], B[k = lane&3][col = lane>>2],
+// C/D[row = lane>>2][col = 2*(lane&3) + {0,1}].
+__device__ __forceinline__ void chd_tile_sub_xyT(double* C, const double* X, const double* Y, int lane) {
+  const int r = lane >> 2, k = lane & 3;
+  double c0 = C[r * 8 + 2 * k], c1 = C[r * 8 + 2 * k + 1];
+#pragma unroll
+  for (int kk = 0; kk < 8; kk += 4) {
+    const double a = -X[r * 8 + kk + k];
+    const double b = Y[r * 8 + kk + k];
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+  }
+  C[r * 8 + 2 * k] = c0;
+  C[r * 8 + 2 * k + 1] = c1;
+}
+
+// In-place LDL^T of the lower triangle of an 8x8 row-major tile by one warp (lanes replicate rows r = lane&7).
+// On exit: strict lower part = unit L, diagonal = d.  dinv[8] receives 1/d.  Returns false on a bad pivot.
+__device__ __forceinline__ bool chd_tile_ldl(double* T, double* dinv, int lane) {
+  const int r = lane & 7;
+  double a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = c <= r ? T[r * 8 + c] : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const double dp = __shfl_sync(0xffffffffu, a[p], p, 8);
+    ok = ok && (fabs(dp) > 1e-300) && isfinite(dp);
+    const double inv = 1.0 / dp;
+    const double lr = a[p] * inv;
+#pragma unroll
+    for (int c = p + 1; c < 8; ++c) {
+      const double acp = __shfl_sync(0xffffffffu, a[p], c, 8);  // unscaled A[c][p]
+      if (r >= c) a[c] -= lr * acp;
+    }
+    if (r > p) a[p] = lr;
+    if (lane == p) dinv[p] = inv;
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c <= r) T[r * 8 + c] = a[c];
+  }
+  return ok;
+}
+
+// One panel row: y = a L0^-T (unit lower L0 in tile T0), x = y * dinv.  Writes x in place, y to yout.
+__device__ __forceinline__ void chd_row_trsm(double* a_row, const double* T0, const double* dinv, double* yout) {
+  double y[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    double v = a_row[c];
+#pragma unroll
+    for (int p = 0; p < c; ++p) v -= y[p] * T0[c * 8 + p];
+    y[c] = v;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    yout[c] = y[c];
+    a_row[c] = y[c] * dinv[c];
+  }
+}
+
+// 16-byte copy global -> window.  With the window in shared memory this is an asynchronous cp.async (LDGSTS);
+// chd_copy_wait() must precede the barrier that publishes the data.
+__device__ __forceinline__ void chd_copy16(double* dst, const double* src, int smem) {
+  if (smem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src) : "memory");
+  } else {
+    dst[0] = src[0];
+    dst[1] = src[1];
+  }
+}
+__device__ __forceinline__ void chd_copy_wait(int smem) {
+  if (smem) asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// window slot of band tile (I, J), I >= J, both inside a sliding window of Q block rows/columns
+__device__ __forceinline__ int chd_win_slot(int I, int J, int Q) {
+  const int a = I % Q, b = J % Q;
+  const int hi = a > b ? a : b, lo = a > b ? b : a;
+  return hi * (hi + 1) / 2 + lo;
+}

@@ -402,8 +402,12 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
     if (sb.var_stance[v] && sb.var_t1[v] - sb.var_t0[v] > span_max) border.push_back(v);
     else keys.push_back({0.5 * (sb.var_t0[v] + sb.var_t1[v]), 0, v});
   }
+  // rows that keep their multiplier as a KKT unknown: equalities, and inequalities with more than 12 slots
+  // (leg length); the others (terrain, friction pyramid, height -- the latter is degenerate with the terrain
+  // equality during stance and is numerically safer condensed) are condensed into the primal block
+  auto explicit_row = [&](int r) { return sb.row_lo[r] == sb.row_hi[r] || sb.ent_ptr[r + 1] - sb.ent_ptr[r] > 12; };
   for (int r = 0; r < h.m; ++r)
-    if (sb.row_lo[r] == sb.row_hi[r]) keys.push_back({sb.row_t[r] + 1e-6, 1, r});
+    if (explicit_row(r)) keys.push_back({sb.row_t[r] + 1e-6, 1, r});
   std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.t < b.t; });
   for (size_t i = 0; i < keys.size(); ++i) (keys[i].kind == 0 ? sb.var_kkt[keys[i].id] : sb.row_kkt[keys[i].id]) = (int)i;
   h.Na = (int)keys.size();
@@ -425,10 +429,11 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
   for (int r = 0; r < h.m; ++r) {
     const int* c = sb.ent_col.data() + sb.ent_ptr[r];
     const int cnt = sb.ent_ptr[r + 1] - sb.ent_ptr[r];
-    if (sb.row_kkt[r] >= 0) {  // equality row: couples the row with each of its variables
+    if (sb.row_kkt[r] >= 0) {  // explicit row: couples the row with each of its variables
       for (int i = 0; i < cnt; ++i) span(c + i, 1, sb.row_kkt[r]);
+      if (sb.row_set[r] == CHD_SET_ROM || sb.row_set[r] == CHD_SET_HEEL) span(c, cnt, -1);  // curvature term y+ Jd^T Jd
     } else {
-      span(c, cnt, -1);        // inequality row: J^T Sigma J clique
+      span(c, cnt, -1);        // condensed inequality row: J^T Sigma J clique
     }
   }
   // cost cliques: data samples (one polynomial) and smoothing samples (polynomials at t and t + dt)

@@ -344,7 +344,7 @@ struct Solver {
       if (it == 0) theta_max = 1e4 * std::max(1.0, theta), theta_min = 1e-4 * std::max(1.0, theta);
       if (mu != mu_filter) filt.clear(), mu_filter = mu;
       // ---- condensed KKT ----
-      for (int r = 0; r < m; ++r) ypos[r] = dist_row[r] ? std::max(sc[r] * y[r], 0.0) : 0.0;
+      for (int r = 0; r < m; ++r) ypos[r] = (dist_row[r] && sc[r] * y[r] > 1e-8) ? sc[r] * y[r] : 0.0;  // CHD_CURV_MIN
       Triplets W1 = hess(true, nullptr), W2 = hess(false, ypos.data());
       w = bandwidth(W1, W2);
       K.init(Na, nb, w);

@@ -41,6 +41,8 @@ def test_layout_matches_oracle(chd, n_ee, seed):
     vk, rk = lay["var_kkt"][0, :n], lay["row_kkt"][0, :m]
     used = np.concatenate([vk[vk >= 0], rk[rk >= 0]])
     assert len(np.unique(used)) == len(used) == Na + nb
+    lo_, hi_ = lay["row_lo"][0, :m], lay["row_hi"][0, :m]
+    assert (rk[lo_ == hi_] >= 0).all()          # every equality row is a KKT unknown
     for r in np.nonzero(rk >= 0)[0]:
         c = col[ptr[r]:ptr[r + 1]]
         k = vk[c[c >= 0]]
