@@ -158,12 +158,16 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   const size_t nbp8 = 8 * (size_t)D.nbt;
   b->smem_eval = (2 * (size_t)hb.n_max + CHD_THREADS) * sizeof(double);
   b->smem_ls = ((size_t)hb.n_max + CHD_THREADS) * sizeof(double);
-  const size_t kkt_fixed = (CHD_KKT_THREADS + (size_t)((hb.n_max + 1) & ~1) + 16 * (size_t)D.nbc_max + nbp8 + nbp8 * nbp8 + 2 * (size_t)(D.Q + D.nbt) * 64 + 16) * sizeof(double);
+  D.pan_doubles = std::max(2 * (D.Q + D.nbt) * 64, 8 * D.nbc_max);
+  cudaFuncAttributes fa;
+  CHD_CUDA(cudaFuncGetAttributes(&fa, chd_k_kkt));
+  const size_t kkt_static = fa.sharedSizeBytes;
+  const size_t kkt_fixed = (CHD_KKT_THREADS + (size_t)((hb.n_max + 1) & ~1) + 8 * (size_t)D.nbc_max + nbp8 + nbp8 * nbp8 + (size_t)D.pan_doubles + 16) * sizeof(double);
   const size_t kkt_win = ((size_t)D.win_tiles * 64 + (size_t)D.Q * D.nbt * 64) * sizeof(double);
   int dev = 0, smem_max = 0;
   CHD_CUDA(cudaGetDevice(&dev));
   CHD_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (kkt_fixed + kkt_win + 1024 <= (size_t)smem_max) {
+  if (kkt_fixed + kkt_win + kkt_static + 256 <= (size_t)smem_max) {
     D.win_smem = 1;
     b->smem_kkt = kkt_fixed + kkt_win;
   } else {
@@ -171,7 +175,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
     b->smem_kkt = kkt_fixed;
     if ((rc = dev_alloc(b, B * (kkt_win / sizeof(double)), &D.scratch))) return rc;
   }
-  if (b->smem_eval + 1024 > (size_t)smem_max || b->smem_kkt + 1024 > (size_t)smem_max) {
+  if (b->smem_eval + 1024 > (size_t)smem_max || b->smem_kkt + kkt_static + 256 > (size_t)smem_max) {
     fprintf(stderr, "libchd: problem too large for the shared-memory staged kernels (n_max=%d)\n", hb.n_max);
     return -5;
   }

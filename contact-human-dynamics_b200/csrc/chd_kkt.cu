@@ -96,8 +96,8 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D, const ChdStageDev&
   double* cc = xs + (8 * D.nbc_max + nbp8);
   double* ypan = cc + nbp8 * nbp8;
   double* xpan = ypan + (Q + nbt) * 64;
-  double* xs2 = xpan + (Q + nbt) * 64;
-  double* dinv = xs2 + 8 * D.nbc_max;
+  double* xs2 = ypan;                    // back-substitution accumulator aliases the (then idle) panel buffers
+  double* dinv = ypan + D.pan_doubles;
   double* win = WS ? dinv + 16 : D.scratch + (size_t)b * ((size_t)D.win_tiles * 64 + (size_t)Q * nbt * 64);
   double* bwin = win + (size_t)D.win_tiles * 64;
   const double sf = I.sf;
