@@ -118,6 +118,28 @@ int chd_phys_reset(chd_phys_batch* b);
 int chd_phys_kernel_times(chd_phys_batch* b, double* ms8, int64_t* launches8, int reset);
 int chd_phys_set_timing(chd_phys_batch* b, int enable);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Foot-contact classifier (src/contact_learning/test.py:51-152 val_full_video + models/openpose_only.py:29-78).
+ * weights: the five Linear weights in torch layout [out][in], concatenated in layer order
+ *          (1024x351, 512x1024, 128x512, 32x128, 20x32); biases concatenated likewise;
+ * bn: for each of the four BatchNorm1d layers gamma, beta, running_mean, running_var (4 x width floats), concatenated.
+ * All [host].  Keys of the reference state_dict: model.{0,3,6,10,13}.{weight,bias}, model.{1,4,7,11}.*. */
+typedef struct chd_contact_net chd_contact_net;
+int chd_contact_create(const float* weights, const float* biases, const float* bn, float bn_eps, int32_t device,
+                       chd_contact_net** out);
+void chd_contact_destroy(chd_contact_net* net);
+/* frames [host]: V x Fmax x 25 x 3 doubles = keypoints after the dataset's preprocessing (pad to the longest video,
+ * scale to 1280 wide, low-confidence interpolation, division by 200.416..., real_video_dataset.py:132-163);
+ * seq_lens [host] V; labels [host] V x Fmax x 4 int64 (columns L heel, L toe, R heel, R toe; rows >= seq_len are 0);
+ * logits [host, optional] V x (Fmax-8) x 20; min_abs_logit [host, optional]: smallest |logit| that entered a vote. */
+int chd_contact_forward(chd_contact_net* net, const double* frames, int32_t V, int32_t Fmax, const int32_t* seq_lens,
+                        int64_t* labels, float* logits, float* min_abs_logit);
+/* Same with every buffer already on the device (stream = cudaStream_t as void*, NULL = the net's own stream). */
+int chd_contact_forward_device(chd_contact_net* net, const double* frames_dev, int32_t V, int32_t Fmax,
+                               const int32_t* seq_lens_dev, int64_t* labels_dev, float* logits_dev, float* min_abs_dev,
+                               void* stream);
+int64_t chd_contact_launch_count(const chd_contact_net* net);
+
 const char* chd_version(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,47 @@
+"""GPU parity tests of the contact classifier (CUDA kernels through the C ABI)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def test_golden_labels_bit_exact(chd):
+    from make_contact_golden import contact_weights
+    g = dict(np.load(os.path.join(HERE, "golden", "contact", "contact_golden.npz")))
+    names = [str(n) for n in g["names"]]
+    frames = np.stack([g["proc_" + n] for n in names])
+    net = chd.contact.ContactNet(contact_weights(0))
+    labels, logits, mabs = net.forward(frames, g["seq_lens"].astype(np.int32), want_logits=True)
+    # fp32 logits: same math, different summation order than the reference's torch forward -> 2e-5 absolute
+    np.testing.assert_allclose(logits, g["logits"], rtol=0, atol=2e-5)
+    for i, n in enumerate(names):
+        L = int(g["seq_lens"][i])
+        np.testing.assert_array_equal(labels[i, :L], g["contacts_" + n])     # integer labels: bit exact
+        assert (labels[i, L:] == 0).all()
+    assert labels.dtype == np.int64 and mabs > 0
+    assert net.launch_count() == 2
+
+
+def test_large_batch_against_torch_reference(chd):
+    from make_contact_golden import contact_weights, synth_keypoints
+    from oracle import contact as oc
+    sd = contact_weights(1)
+    raw = [synth_keypoints(1000 + i, 60 + (i % 7)) for i in range(48)]
+    frames, seq_lens = chd.contact.preprocess_videos(raw)
+    net = chd.contact.ContactNet(sd)
+    labels, logits, mabs = net.forward(frames, seq_lens, want_logits=True)
+    ref_logits = oc.forward_torch(sd, oc.windows_from_frames(frames))
+    np.testing.assert_allclose(logits, ref_logits, rtol=0, atol=5e-5)
+    risky = 0
+    for i in range(len(raw)):
+        ref = oc.vote(ref_logits[i], int(seq_lens[i]))
+        if not np.array_equal(labels[i, :seq_lens[i]], ref):
+            # a flip is only admissible where a logit sits on the decision boundary
+            assert np.abs(ref_logits[i]).min() < 1e-4
+            risky += 1
+    assert risky <= 1
