@@ -88,3 +88,34 @@ def test_solved_trajectories_match_cpu_oracle(chd):
         oracle_iters = [s["iters"] for s in ref["stages"]]
         gpu_iters = [int(out["stage_iters"][s, i]) for s in (0, 1, 2, 3, 5)]
         assert oracle_iters == gpu_iters, (oracle_iters, gpu_iters)
+
+
+def test_four_end_effectors_solve_matches_oracle(chd):
+    """Reference configuration (toes + heels, toe-heel distance equality rows): wide band -> global-scratch window."""
+    from oracle.phys import OracleProblem
+    p = chd.synth.make_problem(2, n_ee=4)
+    b = chd.phys.PhysBatch([p])
+    out = b.solve()
+    assert (out["stage_status"][[0, 1, 2, 3, 5], 0] == 0).all(), out["stage_status"][:, 0]
+    ref = OracleProblem(p).solve()
+    nf = out["frames"][0]
+    got, exp = out["samples"][2, 0, :nf], ref["durations"]
+    np.testing.assert_allclose(got[:, :18], exp[:, :18], rtol=0, atol=1e-5)
+    np.testing.assert_array_equal(got[:, 30:], exp[:, 30:])
+
+
+def test_phys_optim_cli_files(chd, tmp_path):
+    """scripts/phys_optim.py: reference flags, four input files in, four output files out (phys_optim.cpp:23-31,63-153)."""
+    import subprocess, sys, os
+    p = chd.synth.make_problem(4, n_frames=60, n_ee=2)
+    ind, outd = str(tmp_path / "in"), str(tmp_path / "out")
+    os.makedirs(outd)
+    chd.io_formats.write_phys_inputs(p, ind)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(root, "scripts", "phys_optim.py"), "--in_dir", ind, "--nframes", "60",
+                           "--out_dir=" + outd, "--n_ee", "2", "--w_com_lin", "0.4"])
+    for name in ("sol_out_no_dynamics.txt", "sol_out_dynamics.txt", "sol_out_durations.txt", "success_log.txt"):
+        assert os.path.exists(os.path.join(outd, name))
+    r = chd.io_formats.read_solution(os.path.join(outd, "sol_out_durations.txt"))
+    assert r["num_frames"] == 60 and r["num_feet"] == 2 and np.isfinite(r["foot_force"]).all()
+    assert open(os.path.join(outd, "success_log.txt")).read() == "dynamics 1\ndurations 1\n"
