@@ -10,14 +10,16 @@
 #include "chd_dev.h"
 
 // kernels (chd_kernels.cu)
-__global__ void chd_k_stage_begin(ChdDev D, ChdStageDev sg, int max_iter);
-__global__ void chd_k_eval(ChdDev D, ChdStageDev sg, int only_running);
+__global__ void chd_k_stage_begin(ChdDev D);
+__global__ void chd_k_eval(ChdDev D);
 __global__ void chd_k_init(ChdDev D);
-__global__ void chd_k_kkt(ChdDev D, ChdStageDev sg);
-__global__ void chd_k_kkt_gwin(ChdDev D, ChdStageDev sg);
-__global__ void chd_k_hess_base(ChdDev D, ChdStageDev sg);
-__global__ void chd_k_linesearch(ChdDev D, ChdStageDev sg);
+__global__ void chd_k_kkt(ChdDev D);
+__global__ void chd_k_kkt_gwin(ChdDev D);
+__global__ void chd_k_hess_base(ChdDev D);
+__global__ void chd_k_linesearch(ChdDev D);
 __global__ void chd_k_sample(ChdDev D, double* out, int* frames_out);
+__global__ void chd_k_snapshot(ChdDev D, int* frames_out);
+__global__ void chd_k_sched_reset(ChdDev D);
 
 #define CHD_CUDA(x)                                                                          \
   do {                                                                                       \
@@ -47,6 +49,8 @@ struct chd_phys_batch {
   ChdIpm* h_ipm = nullptr;  // pinned
   double* d_x0 = nullptr;
   int64_t h2d_bytes = 0;
+  ChdStageDev* d_stages = nullptr;
+  int sched_max_iter = 0;
 };
 
 namespace {
@@ -72,9 +76,12 @@ int dev_alloc(chd_phys_batch* b, size_t count, T** out) {
   return 0;
 }
 
-ChdStageDev stage_dev(const ChdStageCfg& c) {
+ChdStageDev stage_dev(const ChdStageCfg& c, int stage) {
   ChdStageDev s;
   s.set_mask = c.set_mask;
+  s.max_iter = c.max_iter;
+  s.snap_after = stage == CHD_STAGE_12 ? 0 : (stage == CHD_STAGE_22 ? 1 : ((stage == CHD_STAGE_4 || stage == CHD_STAGE_3) ? 2 : -1));
+  s.pad = 0;
   for (int i = 0; i < 3; ++i) s.w_data[i] = c.w_data[i], s.w_vel[i] = c.w_vel[i], s.w_acc[i] = c.w_acc[i];
   return s;
 }
@@ -98,9 +105,70 @@ struct Timer {
   }
 };
 
-void launch_eval(chd_phys_batch* b, const ChdStageDev& sg, int only_running) {
+void launch_eval(chd_phys_batch* b) {
   Timer t(b, KT_EVAL);
-  chd_k_eval<<<b->hb.B, CHD_THREADS, b->smem_eval, b->stream>>>(b->D, sg, only_running);
+  chd_k_eval<<<b->hb.B, CHD_THREADS, b->smem_eval, b->stream>>>(b->D);
+}
+
+// uploads the stage table (optionally with an iteration-cap override for one stage) and the schedule
+int set_schedule(chd_phys_batch* b, const int* sched, int nsched, int override_stage, int override_max_iter) {
+  ChdStageDev tab[6];
+  for (int s = 0; s < 6; ++s) tab[s] = stage_dev(b->hb.stage[s], s);
+  if (override_stage >= 0 && override_max_iter > 0) tab[override_stage].max_iter = override_max_iter;
+  CHD_CUDA(cudaMemcpyAsync(b->d_stages, tab, sizeof(tab), cudaMemcpyHostToDevice, b->stream));
+  b->D.stages = b->d_stages;
+  b->D.nsched = nsched;
+  for (int i = 0; i < nsched; ++i) b->D.sched[i] = sched[i];
+  b->sched_max_iter = 0;
+  for (int i = 0; i < nsched; ++i) b->sched_max_iter += tab[sched[i]].max_iter + 2;
+  chd_k_sched_reset<<<(b->hb.B + 127) / 128, 128, 0, b->stream>>>(b->D);
+  b->launches++;
+  return 0;
+}
+
+// runs the uploaded schedule to completion: every sequence walks through its stages at its own pace
+int run_schedule(chd_phys_batch* b) {
+  const int B = b->hb.B;
+  const int check_every = 8;
+  for (int it = 0; it <= b->sched_max_iter; ++it) {
+    {
+      Timer t(b, KT_INIT);
+      chd_k_stage_begin<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
+    }
+    launch_eval(b);
+    {
+      Timer t(b, KT_INIT);
+      chd_k_init<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
+    }
+    {
+      Timer t(b, KT_INIT);
+      chd_k_hess_base<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
+    }
+    {
+      Timer t(b, KT_KKT);
+      if (b->D.win_smem) chd_k_kkt<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);
+      else chd_k_kkt_gwin<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);
+    }
+    {
+      Timer t(b, KT_LS);
+      chd_k_linesearch<<<B, CHD_THREADS, b->smem_ls, b->stream>>>(b->D);
+    }
+    {
+      Timer t(b, KT_SAMPLE);
+      chd_k_snapshot<<<B, 128, 0, b->stream>>>(b->D, b->d_frames);
+    }
+    if ((it % check_every) == check_every - 1) {
+      CHD_CUDA(cudaMemcpyAsync(b->h_ipm, b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost, b->stream));
+      CHD_CUDA(cudaStreamSynchronize(b->stream));
+      bool any = false;
+      for (int i = 0; i < B; ++i) any |= (b->h_ipm[i].phase != CHD_PH_FINISHED);
+      if (!any) break;
+    }
+  }
+  CHD_CUDA(cudaMemcpyAsync(b->h_ipm, b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost, b->stream));
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
+  CHD_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace
@@ -189,6 +257,9 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   b->allocs.push_back(b->d_samples);
   b->allocs.push_back(b->d_frames);
   CHD_CUDA(cudaMallocHost((void**)&b->h_ipm, B * sizeof(ChdIpm)));
+  CHD_CUDA(cudaMalloc((void**)&b->d_stages, 6 * sizeof(ChdStageDev)));
+  b->allocs.push_back(b->d_stages);
+  if ((rc = dev_alloc(b, 3 * B * hb.fo_max * stride, &D.snapshots))) return rc;
   *out = b;
   return 0;
 }
@@ -238,12 +309,14 @@ int chd_phys_set_x(chd_phys_batch* b, const double* x) {
 int chd_phys_eval(chd_phys_batch* b, int32_t stage, double* cost, double* grad, double* g, double* jac_vals) {
   if (!b || stage < 0 || stage > 5 || b->host_only) return -1;
   const ChdHostBatch& hb = b->hb;
-  ChdStageDev sg = stage_dev(hb.stage[stage]);
+  int sched[1] = {stage};
+  int rc = set_schedule(b, sched, 1, -1, 0);
+  if (rc) return rc;
   {
     Timer t(b, KT_INIT);
-    chd_k_stage_begin<<<hb.B, CHD_THREADS, 0, b->stream>>>(b->D, sg, 0);
+    chd_k_stage_begin<<<hb.B, CHD_THREADS, 0, b->stream>>>(b->D);
   }
-  launch_eval(b, sg, 0);
+  launch_eval(b);
   CHD_CUDA(cudaStreamSynchronize(b->stream));
   CHD_CUDA(cudaGetLastError());
   const size_t B = hb.B;
@@ -274,56 +347,20 @@ int chd_phys_get_layout(const chd_phys_batch* b, int32_t* ent_ptr, int32_t* ent_
 
 int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int32_t* status, int32_t* iters, double* stats) {
   if (!b || stage < 0 || stage > 5 || b->host_only) return -1;
-  const ChdHostBatch& hb = b->hb;
-  ChdStageDev sg = stage_dev(hb.stage[stage]);
-  if (max_iter <= 0) max_iter = hb.stage[stage].max_iter;
-  const int B = hb.B;
-  {
-    Timer t(b, KT_INIT);
-    chd_k_stage_begin<<<B, CHD_THREADS, 0, b->stream>>>(b->D, sg, max_iter);
-  }
-  launch_eval(b, sg, 0);
-  {
-    Timer t(b, KT_INIT);
-    chd_k_init<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
-  }
-  {
-    Timer t(b, KT_INIT);
-    chd_k_hess_base<<<B, CHD_THREADS, 0, b->stream>>>(b->D, sg);
-  }
-  const int check_every = 8;
-  for (int it = 0; it <= max_iter; ++it) {
-    {
-      Timer t(b, KT_KKT);
-      if (b->D.win_smem) chd_k_kkt<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D, sg);
-      else chd_k_kkt_gwin<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D, sg);
-    }
-    {
-      Timer t(b, KT_LS);
-      chd_k_linesearch<<<B, CHD_THREADS, b->smem_ls, b->stream>>>(b->D, sg);
-    }
-    launch_eval(b, sg, 1);
-    if ((it % check_every) == check_every - 1 || it == max_iter) {
-      CHD_CUDA(cudaMemcpyAsync(b->h_ipm, b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost, b->stream));
-      CHD_CUDA(cudaStreamSynchronize(b->stream));
-      bool any = false;
-      for (int i = 0; i < B; ++i) any |= (b->h_ipm[i].status == 1);
-      if (!any) break;
-    }
-  }
-  CHD_CUDA(cudaMemcpyAsync(b->h_ipm, b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost, b->stream));
-  CHD_CUDA(cudaStreamSynchronize(b->stream));
-  CHD_CUDA(cudaGetLastError());
+  const int B = b->hb.B;
+  int sched[1] = {stage};
+  int rc = set_schedule(b, sched, 1, stage, max_iter);
+  if (rc) return rc;
+  if ((rc = run_schedule(b))) return rc;
   for (int i = 0; i < B; ++i) {
     const ChdIpm& I = b->h_ipm[i];
-    if (status) status[i] = I.status == 1 ? -1 : I.status;
-    if (iters) iters[i] = I.iter;
+    if (status) status[i] = I.st_status[stage];
+    if (iters) iters[i] = I.st_iters[stage];
     if (stats) {
       double* s = stats + 8 * i;
       s[0] = I.f, s[1] = I.E0, s[2] = I.viol_u, s[3] = I.dual_u, s[4] = I.compl_u, s[5] = I.mu, s[6] = I.delta_w, s[7] = I.ls_fail;
     }
-    if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "chd prof (Mcycles) seq0 stage %d: err %.2f jasm %.2f hasm %.2f factor %.2f border %.2f back %.2f rec %.2f | sync-wait after (b) %.2f\n", stage, I.prof[0]/1e6, I.prof[1]/1e6, I.prof[2]/1e6, I.prof[3]/1e6, I.prof[4]/1e6, I.prof[5]/1e6, I.prof[6]/1e6, I.prof[7]/1e6);
-    if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "   worker thread 40: (b) %.2f sync1 %.2f (c) %.2f sync2 %.2f Mcycles\n", I.filt[40]/1e6, I.filt[41]/1e6, I.filt[42]/1e6, I.filt[43]/1e6);
+    if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "chd prof (Mcycles) seq0 stage %d: err %.2f jasm %.2f hasm %.2f factor %.2f border %.2f back %.2f rec %.2f | ldl %.2f\n", stage, I.prof[0]/1e6, I.prof[1]/1e6, I.prof[2]/1e6, I.prof[3]/1e6, I.prof[4]/1e6, I.prof[5]/1e6, I.prof[6]/1e6, I.prof[7]/1e6);
   }
   return 0;
 }
@@ -348,36 +385,32 @@ int chd_phys_sample(chd_phys_batch* b, double* out, int32_t* frames_out) {
   return 0;
 }
 
-// Staged schedule of phys_optim.cpp:554-749.  Stage 3 (phase-duration optimisation) is not yet implemented
-// on the device: like the reference when its stage 3 fails (phys_optim.cpp:713-749) the schedule continues
-// with the fixed-duration stage 4 and reports durations_succeed from it.
+// Staged schedule of phys_optim.cpp:554-749.  Every sequence walks through 1.1, 1.2, 2.1, 2.2, 4 at its own pace
+// (converged sequences do not wait for the slowest one of their stage).  Stage 3 (phase-duration optimisation)
+// is not yet implemented on the device: like the reference when its stage 3 fails (phys_optim.cpp:713-749) the
+// schedule continues with the fixed-duration stage 4 and reports durations_succeed from it.
 int chd_phys_solve(chd_phys_batch* b, double* samples, int32_t* frames_out, int32_t* success, int32_t* stage_status,
                    int32_t* stage_iters) {
   if (!b || b->host_only) return -1;
   const ChdHostBatch& hb = b->hb;
   const int B = hb.B;
   const size_t stride = 6 + 7 * (size_t)hb.n_ee_max, snap = (size_t)B * hb.fo_max * stride;
-  std::vector<int32_t> st(B), itn(B);
-  auto run = [&](int stage) -> int {
-    int rc = chd_phys_solve_stage(b, stage, 0, st.data(), itn.data(), nullptr);
-    if (rc) return rc;
-    if (stage_status) std::memcpy(stage_status + (size_t)stage * B, st.data(), B * sizeof(int32_t));
-    if (stage_iters) std::memcpy(stage_iters + (size_t)stage * B, itn.data(), B * sizeof(int32_t));
-    return 0;
-  };
-  int rc;
-  if (stage_status) std::fill(stage_status, stage_status + 6 * (size_t)B, -9);
-  if (stage_iters) std::fill(stage_iters, stage_iters + 6 * (size_t)B, 0);
-  if ((rc = run(CHD_STAGE_11))) return rc;
-  if ((rc = run(CHD_STAGE_12))) return rc;
-  if (samples && (rc = chd_phys_sample(b, samples, frames_out))) return rc;           // sol_out_no_dynamics
-  if ((rc = run(CHD_STAGE_21))) return rc;
-  if ((rc = run(CHD_STAGE_22))) return rc;
-  if (success) for (int i = 0; i < B; ++i) success[2 * i] = st[i] == 0;             // dynamics_succeed (:655)
-  if (samples && (rc = chd_phys_sample(b, samples + snap, frames_out))) return rc;   // sol_out_dynamics
-  if ((rc = run(CHD_STAGE_4))) return rc;
-  if (success) for (int i = 0; i < B; ++i) success[2 * i + 1] = st[i] == 0;         // durations_succeed (:746)
-  if (samples && (rc = chd_phys_sample(b, samples + 2 * snap, frames_out))) return rc;  // sol_out_durations
+  int sched[5] = {CHD_STAGE_11, CHD_STAGE_12, CHD_STAGE_21, CHD_STAGE_22, CHD_STAGE_4};
+  int rc = set_schedule(b, sched, 5, -1, 0);
+  if (rc) return rc;
+  if (samples) CHD_CUDA(cudaMemsetAsync(b->D.snapshots, 0, 3 * snap * sizeof(double), b->stream));
+  if ((rc = run_schedule(b))) return rc;
+  for (int i = 0; i < B; ++i) {
+    const ChdIpm& I = b->h_ipm[i];
+    if (success) success[2 * i] = I.st_status[CHD_STAGE_22] == 0, success[2 * i + 1] = I.st_status[CHD_STAGE_4] == 0;  // :655, :746
+    for (int s = 0; s < 6; ++s) {
+      if (stage_status) stage_status[(size_t)s * B + i] = I.st_status[s];
+      if (stage_iters) stage_iters[(size_t)s * B + i] = I.st_iters[s];
+    }
+  }
+  if (samples) CHD_CUDA(cudaMemcpyAsync(samples, b->D.snapshots, 3 * snap * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (frames_out) CHD_CUDA(cudaMemcpyAsync(frames_out, b->d_frames, B * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
   return 0;
 }
 

@@ -15,9 +15,15 @@
 #define CHD_ROW_HASU 8
 
 // Interior-point state of one sequence ("chd-ipm").
+#define CHD_PH_BEGIN 0
+#define CHD_PH_RUN 1
+#define CHD_PH_FINISHED 2
 struct ChdIpm {
-  int status;    // 1 running, 0 converged, -1 iteration cap, -2 numerical failure
+  int status;    // of the current stage: 1 running, 0 converged, -1 iteration cap, -2 numerical failure
   int iter, nfilt, ls_fail, max_iter, n_bounds, m_act, pad0;
+  // schedule state: every sequence walks through the staged schedule at its own pace
+  int stage, pos, phase, snap, step_ready, pad1;
+  int st_status[6], st_iters[6];
   double mu, delta_w, sf, theta_max, theta_min, mu_filter, tau;
   double f, E0, viol_u, dual_u, compl_u;          // error measures at the current iterate
   double phi0, theta0, dphi, a_pr, a_du;          // line-search inputs produced by the KKT kernel
@@ -27,6 +33,9 @@ struct ChdIpm {
 
 struct ChdStageDev {
   unsigned set_mask;
+  int max_iter;
+  int snap_after;   // SaveSolution snapshot written when the stage ends (-1: none)
+  int pad;
   double w_data[3], w_vel[3], w_acc[3];
 };
 
@@ -53,6 +62,9 @@ struct ChdDev {
   double* sol;                                // B x (Na_max + nb_max)
   double* scratch;                            // elimination window when it does not fit in shared memory
   ChdIpm* ipm;                                // B
+  const ChdStageDev* stages;                  // 6 stage configurations (device)
+  int sched[8], nsched;                       // stage ids of the running schedule
+  double* snapshots;                          // 3 x B x fo_max x (6 + 7 n_ee_max)
 };
 
 // IPM constants (oracle/ipm_proto.py Opts; IPOPT defaults unless noted)

@@ -14,8 +14,11 @@
 #include "chd_eval.cuh"
 
 // ------------------------------------------------------------------ stage begin -------------------
-__global__ void chd_k_stage_begin(ChdDev D, ChdStageDev sg, int max_iter) {
+__global__ void chd_k_stage_begin(ChdDev D) {
   const int b = blockIdx.x;
+  if (D.ipm[b].phase != CHD_PH_BEGIN) return;
+  const ChdStageDev sg = D.stages[D.ipm[b].stage];
+  const int max_iter = sg.max_iter;
   const ChdSeq* h = D.seq + b;
   int* rf = D.rflag + (size_t)b * D.m_max;
   const double* lo = D.row_lo + (size_t)b * D.m_max;
@@ -52,10 +55,11 @@ __global__ void chd_k_stage_begin(ChdDev D, ChdStageDev sg, int max_iter) {
 
 // ------------------------------------------------------------------ evaluation --------------------
 // dynamic shared memory: x[n_max] | grad[n_max] | red[CHD_THREADS]
-__global__ void __launch_bounds__(CHD_THREADS) chd_k_eval(ChdDev D, ChdStageDev sg, int only_running) {
+__global__ void __launch_bounds__(CHD_THREADS) chd_k_eval(ChdDev D) {
   extern __shared__ double sm[];
   const int b = blockIdx.x;
-  if (only_running && D.ipm[b].status != 1) return;
+  if (D.ipm[b].phase == CHD_PH_FINISHED) return;
+  const ChdStageDev sg = D.stages[D.ipm[b].stage];
   const ChdSeq* h = D.seq + b;
   double* xs = sm;
   double* gs = sm + D.n_max;
@@ -75,6 +79,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_eval(ChdDev D, ChdStageDev 
 __global__ void __launch_bounds__(CHD_THREADS) chd_k_init(ChdDev D) {
   __shared__ double red[CHD_THREADS];
   const int b = blockIdx.x;
+  if (D.ipm[b].phase != CHD_PH_BEGIN) return;
   const ChdSeq* h = D.seq + b;
   const size_t ro = (size_t)b * D.m_max;
   const int* vk = D.var_kkt + (size_t)b * D.n_max;
@@ -138,13 +143,14 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_init(ChdDev D) {
 
 // ------------------------------------------------------------------ line search -------------------
 // dynamic shared memory: xt[n_max] | red[CHD_THREADS]
-__global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D, ChdStageDev sg) {
+__global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D) {
   extern __shared__ double sm[];
   __shared__ int s_ok, s_ftype;
   __shared__ double s_cost;
   const int b = blockIdx.x;
   ChdIpm& I = D.ipm[b];
-  if (I.status != 1) return;
+  if (I.phase != CHD_PH_RUN || !I.step_ready) return;
+  const ChdStageDev sg = D.stages[I.stage];
   const ChdSeq* h = D.seq + b;
   const int n = h->n, m = h->m, tid = threadIdx.x, nt = blockDim.x;
   const size_t ro = (size_t)b * D.m_max, vo = (size_t)b * D.n_max;
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D, ChdSta
   double* gt = D.gt + ro;
   const double mu = I.mu, sf = I.sf, theta = I.theta0, phi0 = I.phi0, dphi = I.dphi, a_pr = I.a_pr, a_du = I.a_du;
   if (a_pr == 0.0 && dphi == 0.0) {  // failed factorisation: nothing to do this iteration
-    if (tid == 0) I.iter += 1;
+    if (tid == 0) I.iter += 1, I.step_ready = 0;
     return;
   }
   ChdCtx c;
@@ -245,14 +251,14 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D, ChdSta
     if (ls == 0) I.delta_w = fmax(I.delta_w / CHD_DW_DEC, CHD_DW_MIN);
     else I.delta_w = fmin(I.delta_w * pow(CHD_DW_INC, (double)min(ls, 3)), CHD_DW_MAX);
     I.iter += 1;
+    I.step_ready = 0;
   }
 }
 
 // ------------------------------------------------------------------ sampling ----------------------
 // SaveSolution (phys_optim.cpp:63-143): t accumulates dt while t <= T + 1e-5.
 // out: B x fo_max x (6 + 7 n_ee_max)
-__global__ void chd_k_sample(ChdDev D, double* out, int* frames_out) {
-  const int b = blockIdx.x;
+__device__ void chd_sample_seq(const ChdDev& D, int b, double* out, int* frames_out) {
   const ChdSeq* h = D.seq + b;
   ChdCtx c;
   chd_make_ctx(D, b, D.x + (size_t)b * D.n_max, c);
@@ -290,4 +296,26 @@ __global__ void chd_k_sample(ChdDev D, double* out, int* frames_out) {
       }
     }
   }
+}
+
+__global__ void chd_k_sample(ChdDev D, double* out, int* frames_out) { chd_sample_seq(D, blockIdx.x, out, frames_out); }
+
+// writes the SaveSolution snapshot of the sequences whose stage just ended (phys_optim.cpp:603,661,758)
+__global__ void chd_k_snapshot(ChdDev D, int* frames_out) {
+  const int b = blockIdx.x;
+  const int snap = D.ipm[b].snap;
+  if (snap < 0) return;
+  const size_t stride = 6 + 7 * (size_t)D.n_ee_max;
+  chd_sample_seq(D, b, D.snapshots + (size_t)snap * D.B * D.fo_max * stride, frames_out);
+  __syncthreads();
+  if (threadIdx.x == 0) D.ipm[b].snap = -1;
+}
+
+// puts every sequence at the start of the schedule D.sched
+__global__ void chd_k_sched_reset(ChdDev D) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= D.B) return;
+  ChdIpm& I = D.ipm[b];
+  I.pos = 0, I.stage = D.sched[0], I.phase = CHD_PH_BEGIN, I.snap = -1, I.step_ready = 0, I.status = 1;
+  for (int q = 0; q < 6; ++q) I.st_status[q] = -9, I.st_iters[q] = 0;
 }

@@ -37,8 +37,10 @@ __device__ void chd_hess_sample(const ChdKT& K, const int* vk, const ChdSpl* P, 
   }
 }
 
-__global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D, ChdStageDev sg) {
+__global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D) {
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  if (D.ipm[b].phase != CHD_PH_BEGIN) return;
+  const ChdStageDev sg = D.stages[D.ipm[b].stage];
   const ChdSeq* h = D.seq + b;
   ChdKT K;
   double* base = D.Kbase + (size_t)b * D.kstride;
@@ -63,18 +65,32 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D, ChdStag
       if (sg.w_acc[cls] != 0.0) chd_hess_sample(K, vk, P, sgn, 2, 1, sf * sg.w_acc[cls]);
     }
   }
+  __syncthreads();
+  if (tid == 0) D.ipm[b].phase = CHD_PH_RUN;
+}
+
+// a stage ended for this sequence: record its outcome, request the snapshot, move on in the schedule
+__device__ __forceinline__ void chd_stage_advance(const ChdDev& D, ChdIpm& I, int status, int snap_after) {
+  I.st_status[I.stage] = status;
+  I.st_iters[I.stage] = I.iter;
+  I.snap = snap_after;
+  I.step_ready = 0;
+  I.pos += 1;
+  if (I.pos < D.nsched) I.stage = D.sched[I.pos], I.phase = CHD_PH_BEGIN;
+  else I.phase = CHD_PH_FINISHED;
 }
 
 // dynamic shared memory layout of chd_k_kkt (doubles):
 //   red[CHD_KKT_THREADS] | vecn[n_max] | xs[Np_max + nbp8] | cc[nbp8*nbp8] | ypan[(Q+nbt)*64] | xpan[(Q+nbt)*64] | xs2[Np_max] | dinv[16]
 //   | win[Q(Q+1)/2 * 64] | bwin[Q*nbt*64]            (the last two in global scratch when they do not fit)
 template <bool WS>
-__device__ __forceinline__ void chd_kkt_body(const ChdDev& D, const ChdStageDev& sg) {
+__device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   extern __shared__ double sm[];
   __shared__ int s_fail;
   const int b = blockIdx.x;
   ChdIpm& I = D.ipm[b];
-  if (I.status != 1) return;
+  if (I.phase != CHD_PH_RUN) return;
+  const ChdStageDev sg = D.stages[I.stage];
   const ChdSeq* h = D.seq + b;
   const int n = h->n, m = h->m, tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
@@ -168,6 +184,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D, const ChdStageDev&
     I.E0 = E0, I.viol_u = violu, I.dual_u = dual_u, I.compl_u = compl_u;
     I.status = new_status;
     s_fail = 0;
+    if (done) chd_stage_advance(D, I, new_status, sg.snap_after);
     if (!done) {
       I.mu = mu;
       I.tau = fmax(CHD_TAU_MIN, 1.0 - mu);
@@ -577,7 +594,8 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D, const ChdStageDev&
       I.delta_w = fmin(fmax(I.delta_w * 100.0, 1e-4), CHD_DW_MAX * 10);
       I.a_pr = 0.0, I.a_du = 0.0, I.dphi = 0.0;
       I.ls_fail += 1;
-      if (I.delta_w > CHD_DW_MAX) I.status = -2;
+      I.step_ready = 1;
+      if (I.delta_w > CHD_DW_MAX) I.status = -2, chd_stage_advance(D, I, -2, sg.snap_after);
     }
     for (int i = tid; i < n; i += nt) D.dx[vo + i] = 0.0;
     for (int r = tid; r < m; r += nt) D.ds[ro + r] = 0.0, D.dy[ro + r] = 0.0, D.dzL[ro + r] = 0.0, D.dzU[ro + r] = 0.0;
@@ -635,10 +653,11 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D, const ChdStageDev&
   if (tid == 0) {
     I.a_pr = a_pr, I.a_du = a_du, I.dphi = dphi;
     I.phi0 = sf * D.cost[2 * b] + phib;
+    I.step_ready = 1;
   }
   CHD_PROF(6);
 }
 
 // the elimination window lives in shared memory (WS) or, for very wide bands, in a global scratch buffer
-__global__ void __launch_bounds__(CHD_KKT_THREADS) chd_k_kkt(ChdDev D, ChdStageDev sg) { chd_kkt_body<true>(D, sg); }
-__global__ void __launch_bounds__(CHD_KKT_THREADS) chd_k_kkt_gwin(ChdDev D, ChdStageDev sg) { chd_kkt_body<false>(D, sg); }
+__global__ void __launch_bounds__(CHD_KKT_THREADS) chd_k_kkt(ChdDev D) { chd_kkt_body<true>(D); }
+__global__ void __launch_bounds__(CHD_KKT_THREADS) chd_k_kkt_gwin(ChdDev D) { chd_kkt_body<false>(D); }
