@@ -238,6 +238,12 @@ def main():
         ach = running_launch_bytes / (kkt_ms / max(kkt_n, 1) * 1e-3) / 1e9 if kkt_n else 0.0
         eval_bytes = float((8 * (2 * sz[:, 0] + 2 * sz[:, 1] + sz[:, 2] + (18 + 3 * N_EE) * FRAMES)).sum())
         eval_ach = eval_bytes / (eval_ms / max(eval_n, 1) * 1e-3) / 1e9 if eval_n else 0.0
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kkt_ncu.json")))
+            traffic = prof["dram_bytes_per_sequence_per_launch"] * B   # ncu --set full capture (profiles/r1_kkt_ncu_summary.md), per launch
+        except Exception:
+            pass
         kkt_flops = float((sz[:, 3] * (sz[:, 5].astype(np.float64) ** 2 + 2.0 * sz[:, 5] * (sz[:, 4] + 1) + (sz[:, 4] + 1.0) ** 2)).sum())
         line = {
             "metric": "optimised frames/sec (batched phys-optim)", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -252,7 +258,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "chd_k_kkt", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": running_launch_bytes, "peak_source": peak_src,
                          "note": "fp64-FMA / latency bound kernel (DESIGN.md); HBM fraction reported as the contract asks",
                          "ms_per_launch": kkt_ms / max(kkt_n, 1), "fp64_gflops": kkt_flops * 2 / (kkt_ms / max(kkt_n, 1) * 1e-3) / 1e9},
             "kernels": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
