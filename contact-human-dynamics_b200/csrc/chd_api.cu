@@ -230,7 +230,8 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   cudaFuncAttributes fa;
   CHD_CUDA(cudaFuncGetAttributes(&fa, chd_k_kkt));
   const size_t kkt_static = fa.sharedSizeBytes;
-  const size_t kkt_fixed = (CHD_KKT_THREADS + (size_t)((hb.n_max + 1) & ~1) + 8 * (size_t)D.nbc_max + nbp8 + nbp8 * nbp8 + (size_t)D.pan_doubles + 16) * sizeof(double);
+  const size_t n_even = (size_t)((hb.n_max + 1) & ~1), xs_len = 8 * (size_t)D.nbc_max + nbp8;
+  const size_t kkt_fixed = (CHD_KKT_THREADS + n_even + xs_len + nbp8 * nbp8 + (size_t)D.pan_doubles + 16) * sizeof(double);
   const size_t kkt_win = ((size_t)D.win_tiles * 64 + (size_t)D.Q * D.nbt * 64) * sizeof(double);
   int dev = 0, smem_max = 0;
   CHD_CUDA(cudaGetDevice(&dev));
@@ -239,9 +240,16 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
     D.win_smem = 1;
     b->smem_kkt = kkt_fixed + kkt_win;
   } else {
+    // long horizons / wide bands: vectors and window in a global scratch area (chd_k_kkt_gwin)
     D.win_smem = 0;
-    b->smem_kkt = kkt_fixed;
-    if ((rc = dev_alloc(b, B * (kkt_win / sizeof(double)), &D.scratch))) return rc;
+    D.pan_doubles = 2 * (D.Q + D.nbt) * 64;
+    b->smem_kkt = (CHD_KKT_THREADS + nbp8 * nbp8 + (size_t)D.pan_doubles + 16) * sizeof(double);
+    D.scratch_stride = n_even + xs_len + 8 * (size_t)D.nbc_max + kkt_win / sizeof(double);
+    if ((rc = dev_alloc(b, B * D.scratch_stride, &D.scratch))) return rc;
+    if (D.Q - 1 + D.nbt > 76) {
+      fprintf(stderr, "libchd: band + border too wide for the pair tables (Q=%d nbt=%d)\n", D.Q, D.nbt);
+      return -5;
+    }
   }
   if (b->smem_eval + 1024 > (size_t)smem_max || b->smem_kkt + kkt_static + 256 > (size_t)smem_max) {
     fprintf(stderr, "libchd: problem too large for the shared-memory staged kernels (n_max=%d)\n", hb.n_max);

@@ -60,7 +60,8 @@ struct ChdDev {
   double* Kwork;                              // B x kstride  KKT matrix of the current iteration, overwritten by its factors
   double* Kbase;                              // B x kstride  per-stage constant part (Gauss-Newton cost Hessian)
   double* sol;                                // B x (Na_max + nb_max)
-  double* scratch;                            // elimination window when it does not fit in shared memory
+  double* scratch;                            // per-sequence vectors + elimination window when they do not fit in shared memory
+  size_t scratch_stride;                      // doubles per sequence in `scratch`
   ChdIpm* ipm;                                // B
   const ChdStageDev* stages;                  // 6 stage configurations (device)
   int sched[8], nsched;                       // stage ids of the running schedule

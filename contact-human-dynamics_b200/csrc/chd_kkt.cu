@@ -106,15 +106,20 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   double* kw = D.Kwork + (size_t)b * D.kstride;
   chd_kt_init(D, h, kw, K);
   const int Q = K.Q, nbt = K.nbt, nbp8 = K.nbp8, NBR = K.nbr, nbl = h->nb, nbc = K.nbc;
+  // WS: everything in shared memory.  !WS (long horizons / very wide bands): only the reduction buffer, the
+  // corner and the panel buffers stay in shared memory; the per-unknown vectors and the window live in a global
+  // (L2 resident) scratch area  vecn | xs | xs2 | win | bwin.
+  const size_t n_even = (size_t)((D.n_max + 1) & ~1), xs_len = (size_t)(8 * D.nbc_max + nbp8);
+  double* gs = WS ? nullptr : D.scratch + (size_t)b * D.scratch_stride;
   double* red = sm;
-  double* vecn = red + CHD_KKT_THREADS;
-  double* xs = vecn + ((D.n_max + 1) & ~1);   // keep 16-byte alignment for cp.async targets
-  double* cc = xs + (8 * D.nbc_max + nbp8);
+  double* vecn = WS ? red + CHD_KKT_THREADS : gs;
+  double* xs = vecn + n_even;                 // keep 16-byte alignment for cp.async targets
+  double* cc = WS ? xs + xs_len : red + CHD_KKT_THREADS;
   double* ypan = cc + nbp8 * nbp8;
   double* xpan = ypan + (Q + nbt) * 64;
-  double* xs2 = ypan;                    // back-substitution accumulator aliases the (then idle) panel buffers
+  double* xs2 = WS ? ypan : xs + xs_len;      // back-substitution accumulator (WS: aliases the then idle panel buffers)
   double* dinv = ypan + D.pan_doubles;
-  double* win = WS ? dinv + 16 : D.scratch + (size_t)b * ((size_t)D.win_tiles * 64 + (size_t)Q * nbt * 64);
+  double* win = WS ? dinv + 16 : xs2 + 8 * (size_t)D.nbc_max;
   double* bwin = win + (size_t)D.win_tiles * 64;
   const double sf = I.sf;
   double mu = I.mu;

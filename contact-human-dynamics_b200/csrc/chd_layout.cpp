@@ -388,69 +388,84 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
   h.nslots = (int)sb.ent_col.size();
 
   // ---- KKT ordering: time-sorted band + border of long-lived (stance) variables ----
-  const double span_max = 0.15;
-  struct Key {
-    double t;
-    int kind, id;
-  };
-  std::vector<Key> keys;
-  std::vector<int> border;
-  sb.var_kkt.assign(h.n, -1);
-  sb.row_kkt.assign(h.m, -1);
-  for (int v = 0; v < h.n; ++v) {
-    if (sb.var_fixed[v]) continue;
-    if (sb.var_stance[v] && sb.var_t1[v] - sb.var_t0[v] > span_max) border.push_back(v);
-    else keys.push_back({0.5 * (sb.var_t0[v] + sb.var_t1[v]), 0, v});
-  }
-  // rows that keep their multiplier as a KKT unknown: equalities, and inequalities with more than 12 slots
-  // (leg length); the others (terrain, friction pyramid, height -- the latter is degenerate with the terrain
-  // equality during stance and is numerically safer condensed) are condensed into the primal block
-  auto explicit_row = [&](int r) { return sb.row_lo[r] == sb.row_hi[r] || sb.ent_ptr[r + 1] - sb.ent_ptr[r] > 12; };
-  for (int r = 0; r < h.m; ++r)
-    if (explicit_row(r)) keys.push_back({sb.row_t[r] + 1e-6, 1, r});
-  std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.t < b.t; });
-  for (size_t i = 0; i < keys.size(); ++i) (keys[i].kind == 0 ? sb.var_kkt[keys[i].id] : sb.row_kkt[keys[i].id]) = (int)i;
-  h.Na = (int)keys.size();
-  h.nb = (int)border.size();
-  for (int j = 0; j < h.nb; ++j) sb.var_kkt[border[j]] = h.Na + j;
-  // half bandwidth from the coupling cliques
-  int w = 0;
-  auto span = [&](const int* cols, int cnt, int rowpos) {
-    int lo = 1 << 30, hi = -1;
-    for (int i = 0; i < cnt; ++i) {
-      if (cols[i] < 0) continue;
-      int k = sb.var_kkt[cols[i]];
-      if (k < 0 || k >= h.Na) continue;
-      lo = std::min(lo, k), hi = std::max(hi, k);
+  // Stance variables living longer than `span_max` go to the dense border, the others into the band.  The best
+  // threshold depends on the gait: long stances (walking, ~0.6 s) belong in the border, the 0.13-0.33 s stances of
+  // densely switching contacts fit inside the band's natural width.  Candidates are scored by the tile work of one
+  // factorisation, block columns x (band groups + border groups)^2.
+  auto order_kkt = [&](double span_max) -> double {
+    struct Key {
+      double t;
+      int kind, id;
+    };
+    std::vector<Key> keys;
+    std::vector<int> border;
+    sb.var_kkt.assign(h.n, -1);
+    sb.row_kkt.assign(h.m, -1);
+    for (int v = 0; v < h.n; ++v) {
+      if (sb.var_fixed[v]) continue;
+      if (sb.var_stance[v] && sb.var_t1[v] - sb.var_t0[v] > span_max) border.push_back(v);
+      else keys.push_back({0.5 * (sb.var_t0[v] + sb.var_t1[v]), 0, v});
     }
-    if (rowpos >= 0) lo = std::min(lo, rowpos), hi = std::max(hi, rowpos);
-    if (hi >= 0) w = std::max(w, hi - lo);
-  };
-  for (int r = 0; r < h.m; ++r) {
-    const int* c = sb.ent_col.data() + sb.ent_ptr[r];
-    const int cnt = sb.ent_ptr[r + 1] - sb.ent_ptr[r];
-    if (sb.row_kkt[r] >= 0) {  // explicit row: couples the row with each of its variables
-      for (int i = 0; i < cnt; ++i) span(c + i, 1, sb.row_kkt[r]);
-      if (sb.row_set[r] == CHD_SET_ROM || sb.row_set[r] == CHD_SET_HEEL) span(c, cnt, -1);  // curvature term y+ Jd^T Jd
-    } else {
-      span(c, cnt, -1);        // condensed inequality row: J^T Sigma J clique
-    }
-  }
-  // cost cliques: data samples (one polynomial) and smoothing samples (polynomials at t and t + dt)
-  for (int s = 0; s < 2 + n_ee; ++s) {
-    for (int i = 0; i < F; ++i) {
-      int cols[24], cnt = 0;
-      double tl;
-      int poly = chd_locate(tend[s].data(), sb.sp[s].npoly(), sb.t_data[i], &tl);
-      for (int q = 0; q < 12; ++q) cols[cnt++] = sb.sp[s].var[poly * 6 + q];
-      if (i < h.n_smooth) {
-        int poly2 = chd_locate(tend[s].data(), sb.sp[s].npoly(), sb.t_data[i] + p.dt, &tl);
-        for (int q = 0; q < 12; ++q) cols[cnt++] = sb.sp[s].var[poly2 * 6 + q];
+    // rows that keep their multiplier as a KKT unknown: equalities, and inequalities with more than 12 slots
+    // (leg length); the others (terrain, friction pyramid, height -- the latter is degenerate with the terrain
+    // equality during stance and is numerically safer condensed) are condensed into the primal block
+    auto explicit_row = [&](int r) { return sb.row_lo[r] == sb.row_hi[r] || sb.ent_ptr[r + 1] - sb.ent_ptr[r] > 12; };
+    for (int r = 0; r < h.m; ++r)
+      if (explicit_row(r)) keys.push_back({sb.row_t[r] + 1e-6, 1, r});
+    std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.t < b.t; });
+    for (size_t i = 0; i < keys.size(); ++i) (keys[i].kind == 0 ? sb.var_kkt[keys[i].id] : sb.row_kkt[keys[i].id]) = (int)i;
+    h.Na = (int)keys.size();
+    h.nb = (int)border.size();
+    for (int j = 0; j < h.nb; ++j) sb.var_kkt[border[j]] = h.Na + j;
+    // half bandwidth from the coupling cliques
+    int w = 0;
+    auto span = [&](const int* cols, int cnt, int rowpos) {
+      int lo = 1 << 30, hi = -1;
+      for (int i = 0; i < cnt; ++i) {
+        if (cols[i] < 0) continue;
+        int k = sb.var_kkt[cols[i]];
+        if (k < 0 || k >= h.Na) continue;
+        lo = std::min(lo, k), hi = std::max(hi, k);
       }
-      span(cols, cnt, -1);
+      if (rowpos >= 0) lo = std::min(lo, rowpos), hi = std::max(hi, rowpos);
+      if (hi >= 0) w = std::max(w, hi - lo);
+    };
+    for (int r = 0; r < h.m; ++r) {
+      const int* c = sb.ent_col.data() + sb.ent_ptr[r];
+      const int cnt = sb.ent_ptr[r + 1] - sb.ent_ptr[r];
+      if (sb.row_kkt[r] >= 0) {  // explicit row: couples the row with each of its variables
+        for (int i = 0; i < cnt; ++i) span(c + i, 1, sb.row_kkt[r]);
+        if (sb.row_set[r] == CHD_SET_ROM || sb.row_set[r] == CHD_SET_HEEL) span(c, cnt, -1);  // curvature term y+ Jd^T Jd
+      } else {
+        span(c, cnt, -1);        // condensed inequality row: J^T Sigma J clique
+      }
     }
+    // cost cliques: data samples (one polynomial) and smoothing samples (polynomials at t and t + dt)
+    for (int s = 0; s < 2 + n_ee; ++s) {
+      for (int i = 0; i < F; ++i) {
+        int cols[24], cnt = 0;
+        double tl;
+        int poly = chd_locate(tend[s].data(), sb.sp[s].npoly(), sb.t_data[i], &tl);
+        for (int q = 0; q < 12; ++q) cols[cnt++] = sb.sp[s].var[poly * 6 + q];
+        if (i < h.n_smooth) {
+          int poly2 = chd_locate(tend[s].data(), sb.sp[s].npoly(), sb.t_data[i] + p.dt, &tl);
+          for (int q = 0; q < 12; ++q) cols[cnt++] = sb.sp[s].var[poly2 * 6 + q];
+        }
+        span(cols, cnt, -1);
+      }
+    }
+    h.w = w;
+    const double grp = (w + 7) / 8 + 1 + (h.nb + 1 + 7) / 8;
+    return (double)((h.Na + 7) / 8) * grp * grp;
+  };
+  const double cand[4] = {0.15, 0.35, 0.5, 1e30};
+  int best = 0;
+  double best_cost = 0;
+  for (int ci = 0; ci < 4; ++ci) {
+    const double cst = order_kkt(cand[ci]);
+    if (ci == 0 || cst < 0.9 * best_cost) best = ci, best_cost = cst;   // leave the default unless clearly better
   }
-  h.w = w;
+  order_kkt(cand[best]);
   return 0;
 }
 

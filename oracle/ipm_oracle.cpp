@@ -294,6 +294,8 @@ struct Solver {
     double E0 = 0, violu = 0, dual_u = 0, compl_u = 0;
     std::vector<double> rx(n), dx(n), ds(m), dy(m), dzL(m), dzU(m), sol, ypos(m), xt(n), ct;
     Arrow K;
+    const int exp_ndur = getenv("CHD_NDUR") ? atoi(getenv("CHD_NDUR")) : 0;
+    const double exp_dreg = getenv("CHD_DREG") ? atof(getenv("CHD_DREG")) : 0.0;
     for (it = 0;; ++it) {
       // ---- error measures ----
       for (int i = 0; i < n; ++i) rx[i] = sf * g[i];
@@ -349,7 +351,7 @@ struct Solver {
       w = bandwidth(W1, W2);
       K.init(Na, nb, w);
       for (int i = 0; i < n; ++i)
-        if (vk[i] >= 0) K.add(vk[i], vk[i], delta_w), K.rhs[vk[i]] += -sf * g[i];
+        if (vk[i] >= 0) K.add(vk[i], vk[i], delta_w + (i >= n - exp_ndur ? exp_dreg : 0.0)), K.rhs[vk[i]] += -sf * g[i];
       for (size_t k = 0; k < W1.v.size(); ++k) {
         int a = vk[W1.r[k]], b = vk[W1.c[k]];
         if (a >= 0 && b >= 0 && a >= b) K.add(a, b, sf * W1.v[k]);
