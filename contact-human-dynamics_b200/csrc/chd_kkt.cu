@@ -471,6 +471,55 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       }
       const bool compact = Gm <= 32;
       const int np_loop = compact ? na * (na + 1) / 2 : npairs;
+      if (!WS) {
+        // window in global (L2) memory: every tile access is a long-latency load, so each warp collects up to four
+        // target tiles, issues all their loads, and only then runs the tensor-core updates and the stores
+        const int r8 = (lane >> 2) * 8 + 2 * (lane & 3);
+        int p = warp - 1;
+        while (p < np_loop) {
+          double* Cp[4];
+          const double *Xp[4], *Yp[4];
+          int nq = 0;
+          while (nq < 4 && p < np_loop) {
+            const int ai = s_pairs[p] >> 8, aj = s_pairs[p] & 255;
+            p += nwarp - 1;
+            int gi, gj;
+            if (compact) {
+              gi = __shfl_sync(0xffffffffu, myg, ai), gj = __shfl_sync(0xffffffffu, myg, aj);
+            } else {
+              gi = ai, gj = aj;
+              if ((gi < GB && gi >= tq) || (gj < GB && gj >= tq) || !gnz[gi] || !gnz[gj]) continue;
+            }
+            if (gi == 0 && gj == 0) continue;
+            const double* X = xpan + gi * 64;
+            const double* Y = ypan + gj * 64;
+            if (gi < GB) {
+              Cp[nq] = win + (size_t)tri(rs[gi], rs[gj]) * 64, Xp[nq] = X, Yp[nq] = Y, ++nq;
+            } else if (gj < GB) {
+              Cp[nq] = bwin + ((size_t)rs[gj] * nbt + (gi - GB)) * 64, Xp[nq] = X, Yp[nq] = Y, ++nq;
+            } else {
+              const int bi = gi - GB, bj = gj - GB;
+              for (int e = lane; e < 64; e += 32) {
+                const int r = e >> 3, cq = e & 7;
+                double acc = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) acc += X[r * 8 + kk] * Y[cq * 8 + kk];
+                cc[(bi * 8 + r) * nbp8 + bj * 8 + cq] -= acc;
+              }
+            }
+          }
+          double c0[4], c1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < nq) c0[i] = Cp[i][r8], c1[i] = Cp[i][r8 + 1];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < nq) {
+              chd_tile_mma(c0[i], c1[i], Xp[i], Yp[i], lane);
+              Cp[i][r8] = c0[i], Cp[i][r8 + 1] = c1[i];
+            }
+        }
+      } else
       for (int p = warp - 1; p < np_loop; p += nwarp - 1) {
         const int ai = s_pairs[p] >> 8, aj = s_pairs[p] & 255;
         int gi, gj;

@@ -54,9 +54,9 @@ __device__ __forceinline__ void chd_radd(const ChdKT& K, int i, double v) {  // 
 // D(8x8) = C - X * Y^T for row-major 8x8 tiles X, Y (fp64 tensor core, two k-steps of m8n8k4).
 // Fragment layout (PTX ISA, mma.m8n8k4 f64): A[row = lane>>2][k = lane&3], B[k = lane&3][col = lane>>2],
 // C/D[row = lane>>2][col = 2*(lane&3) + {0,1}].
-__device__ __forceinline__ void chd_tile_sub_xyT(double* C, const double* X, const double* Y, int lane) {
+// accumulator form: (c0, c1) -= (X Y^T)[r][2k, 2k+1]
+__device__ __forceinline__ void chd_tile_mma(double& c0, double& c1, const double* X, const double* Y, int lane) {
   const int r = lane >> 2, k = lane & 3;
-  double c0 = C[r * 8 + 2 * k], c1 = C[r * 8 + 2 * k + 1];
 #pragma unroll
   for (int kk = 0; kk < 8; kk += 4) {
     const double a = -X[r * 8 + kk + k];
@@ -65,6 +65,11 @@ __device__ __forceinline__ void chd_tile_sub_xyT(double* C, const double* X, con
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
   }
+}
+__device__ __forceinline__ void chd_tile_sub_xyT(double* C, const double* X, const double* Y, int lane) {
+  const int r = lane >> 2, k = lane & 3;
+  double c0 = C[r * 8 + 2 * k], c1 = C[r * 8 + 2 * k + 1];
+  chd_tile_mma(c0, c1, X, Y, lane);
   C[r * 8 + 2 * k] = c0;
   C[r * 8 + 2 * k + 1] = c1;
 }
