@@ -329,6 +329,12 @@ struct Solver {
       E0 = std::max(std::max(dual_inf / s_d, cviol), compl_err(0.0) / s_c);
       dual_u = dual_inf / sf, compl_u = compl_err(0.0) / sf;
       if (verbose) printf("it %3d f %.6e E0 %.2e viol %.2e dual %.2e mu %.1e dw %.1e\n", it, f, E0, violu, dual_inf, mu, delta_w);
+      if (verbose > 2) {
+        int im = 0; double nrm = 0; int cnt = 0;
+        for (int i = 0; i < n; ++i) if (!fixed[i]) { if (std::fabs(rx[i]) > std::fabs(rx[im]) || fixed[im]) im = i; nrm += rx[i] * rx[i]; cnt += std::fabs(rx[i]) > 0.1 * dual_inf; }
+        double ymax = 0; int iy = 0; for (int r = 0; r < m; ++r) if (std::fabs(y[r]) > ymax) ymax = std::fabs(y[r]), iy = r;
+        printf("      argmax rx %d (%.3e) l2 %.3e count>10%% %d | ymax %.3e at row %d | s_d %.3e\n", im, rx[im], std::sqrt(nrm), cnt, ymax, iy, s_d);
+      }
       if (E0 <= o.tol && violu <= o.constr_viol_tol && dual_u <= o.dual_inf_tol && compl_u <= o.compl_inf_tol) {
         status = 0;
         break;
@@ -427,6 +433,7 @@ struct Solver {
       const double phi0 = sf * f + phib;
       // ---- filter line search ----
       double alpha = a_pr, ft = f;
+      if (verbose > 1) printf("      a_pr %.3e a_du %.3e dphi %.3e\n", a_pr, a_du, dphi);
       bool accepted = false, ftype = false;
       int ls = 0;
       for (ls = 0; ls < o.max_backtrack; ++ls) {
