@@ -15,6 +15,7 @@ __global__ void chd_k_eval(ChdDev D);
 __global__ void chd_k_init(ChdDev D);
 __global__ void chd_k_kkt(ChdDev D);
 __global__ void chd_k_kkt_gwin(ChdDev D);
+__global__ void chd_k_kcopy(ChdDev D);
 __global__ void chd_k_hess_base(ChdDev D);
 __global__ void chd_k_linesearch(ChdDev D);
 __global__ void chd_k_sample(ChdDev D, double* out, int* frames_out);
@@ -36,7 +37,8 @@ struct chd_phys_batch {
   ChdHostBatch hb;
   ChdDev D;
   std::vector<void*> allocs;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_kkt = nullptr, ev_copy = nullptr;
   int64_t launches = 0;
   int timing = 0;
   bool host_only = false;
@@ -46,6 +48,7 @@ struct chd_phys_batch {
   int* d_frames = nullptr;
   double* d_samples = nullptr;
   size_t smem_eval = 0, smem_kkt = 0, smem_ls = 0;
+  int kcopy_blocks = 1;
   ChdIpm* h_ipm = nullptr;  // pinned
   double* d_x0 = nullptr;
   int64_t h2d_bytes = 0;
@@ -144,11 +147,18 @@ int run_schedule(chd_phys_batch* b) {
       Timer t(b, KT_INIT);
       chd_k_hess_base<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
     }
+    if (it > 0) CHD_CUDA(cudaStreamWaitEvent(b->stream, b->ev_copy, 0));   // Kwork refreshed by the side stream
     {
       Timer t(b, KT_KKT);
       if (b->D.win_smem) chd_k_kkt<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);
       else chd_k_kkt_gwin<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);
     }
+    // Kwork <- Kbase for the next iteration, overlapped with the line search / evaluation kernels
+    CHD_CUDA(cudaEventRecord(b->ev_kkt, b->stream));
+    CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_kkt, 0));
+    chd_k_kcopy<<<dim3(b->kcopy_blocks, B), 256, 0, b->copy_stream>>>(b->D);
+    b->launches++;
+    CHD_CUDA(cudaEventRecord(b->ev_copy, b->copy_stream));
     {
       Timer t(b, KT_LS);
       chd_k_linesearch<<<B, CHD_THREADS, b->smem_ls, b->stream>>>(b->D);
@@ -167,6 +177,7 @@ int run_schedule(chd_phys_batch* b) {
   }
   CHD_CUDA(cudaMemcpyAsync(b->h_ipm, b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost, b->stream));
   CHD_CUDA(cudaStreamSynchronize(b->stream));
+  CHD_CUDA(cudaStreamSynchronize(b->copy_stream));
   CHD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -203,6 +214,9 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   D.Na_max = hb.Na_max, D.nb_max = hb.nb_max, D.w_max = hb.w_max, D.par_stride = hb.par_stride(), D.n_ee_max = hb.n_ee_max;
   D.fo_max = hb.fo_max, D.Ph_max = hb.Ph_max;
   CHD_CUDA(cudaStreamCreate(&b->stream));
+  CHD_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+  CHD_CUDA(cudaEventCreateWithFlags(&b->ev_kkt, cudaEventDisableTiming));
+  CHD_CUDA(cudaEventCreateWithFlags(&b->ev_copy, cudaEventDisableTiming));
   CHD_CUDA(cudaEventCreate(&b->ev0));
   CHD_CUDA(cudaEventCreate(&b->ev1));
 #define UP(field) if ((rc = dev_upload(b, hb.field, &D.field))) return rc;
@@ -218,6 +232,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   D.nbt = (hb.nb_max + 1 + 7) / 8;
   D.win_tiles = std::max(D.Q * (D.Q + 1) / 2, 2 * D.Q);
   D.kstride = (size_t)D.nbc_max * D.Q * 64 + (size_t)D.nbc_max * D.nbt * 64 + (size_t)64 * D.nbt * D.nbt;
+  b->kcopy_blocks = (int)std::min<size_t>(512, std::max<size_t>(std::max<size_t>(1, 592 / B), D.kstride * sizeof(double) / 131072));
   AL(cost, B * 2) AL(Kwork, B * D.kstride) AL(Kbase, B * D.kstride) AL(sol, B * (size_t)(hb.Na_max + hb.nb_max)) AL(ipm, B)
 #undef AL
   if ((rc = dev_upload(b, hb.x0, (const double**)&b->d_x0))) return rc;
@@ -278,6 +293,9 @@ void chd_phys_batch_destroy(chd_phys_batch* b) {
   if (b->h_ipm) cudaFreeHost(b->h_ipm);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->ev_kkt) cudaEventDestroy(b->ev_kkt);
+  if (b->ev_copy) cudaEventDestroy(b->ev_copy);
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }

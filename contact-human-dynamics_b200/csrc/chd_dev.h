@@ -22,7 +22,8 @@ struct ChdIpm {
   int status;    // of the current stage: 1 running, 0 converged, -1 iteration cap, -2 numerical failure
   int iter, nfilt, ls_fail, max_iter, n_bounds, m_act, pad0;
   // schedule state: every sequence walks through the staged schedule at its own pace
-  int stage, pos, phase, snap, step_ready, pad1;
+  int stage, pos, phase, snap, step_ready;
+  int kw_req;   // the KKT kernel asks for Kwork <- Kbase to be refreshed by the side-stream copy before its next launch
   int st_status[6], st_iters[6];
   double mu, delta_w, sf, theta_max, theta_min, mu_filter, tau;
   double f, E0, viol_u, dual_u, compl_u;          // error measures at the current iterate

@@ -75,6 +75,7 @@ __device__ __forceinline__ void chd_stage_advance(const ChdDev& D, ChdIpm& I, in
   I.st_iters[I.stage] = I.iter;
   I.snap = snap_after;
   I.step_ready = 0;
+  I.kw_req = 0;
   I.pos += 1;
   if (I.pos < D.nsched) I.stage = D.sched[I.pos], I.phase = CHD_PH_BEGIN;
   else I.phase = CHD_PH_FINISHED;
@@ -208,7 +209,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   // (J^T Sigma J); wide ones (leg length) keep their multiplier as an unknown with diagonal
   // -1/Sigma, which needs 36 instead of 666 matrix updates per row.  The right-hand side is accumulated in
   // shared memory (xs) and written out once.
-  {
+  if (!I.kw_req) {   // first iteration of a stage; afterwards chd_k_kcopy refreshes Kwork on the side stream
     const double* base = D.Kbase + (size_t)b * D.kstride;
     const double2* src = reinterpret_cast<const double2*>(base);
     double2* dst = reinterpret_cast<double2*>(kw);
@@ -649,6 +650,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       I.a_pr = 0.0, I.a_du = 0.0, I.dphi = 0.0;
       I.ls_fail += 1;
       I.step_ready = 1;
+      I.kw_req = 1;
       if (I.delta_w > CHD_DW_MAX) I.status = -2, chd_stage_advance(D, I, -2, sg.snap_after);
     }
     for (int i = tid; i < n; i += nt) D.dx[vo + i] = 0.0;
@@ -708,8 +710,27 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     I.a_pr = a_pr, I.a_du = a_du, I.dphi = dphi;
     I.phi0 = sf * D.cost[2 * b] + phib;
     I.step_ready = 1;
+    I.kw_req = 1;
   }
   CHD_PROF(6);
+}
+
+// Kwork <- Kbase for the sequences whose KKT kernel asked for it; runs on a side stream, overlapped with the line
+// search / evaluation kernels of the next iteration, on the SMs the one-CTA-per-sequence kernels leave idle
+__global__ void __launch_bounds__(256) chd_k_kcopy(ChdDev D) {
+  const int b = blockIdx.y;
+  if (!D.ipm[b].kw_req) return;
+  const size_t cnt2 = D.kstride / 2, per = (cnt2 + gridDim.x - 1) / gridDim.x;
+  const size_t lo = (size_t)blockIdx.x * per, hi = lo + per < cnt2 ? lo + per : cnt2;
+  const double2* src = reinterpret_cast<const double2*>(D.Kbase + (size_t)b * D.kstride);
+  double2* dst = reinterpret_cast<double2*>(D.Kwork + (size_t)b * D.kstride);
+  const size_t nt = blockDim.x;
+  size_t i = lo + threadIdx.x;
+  for (; i + 3 * nt < hi; i += 4 * nt) {
+    const double2 v0 = src[i], v1 = src[i + nt], v2 = src[i + 2 * nt], v3 = src[i + 3 * nt];
+    dst[i] = v0, dst[i + nt] = v1, dst[i + 2 * nt] = v2, dst[i + 3 * nt] = v3;
+  }
+  for (; i < hi; i += nt) dst[i] = src[i];
 }
 
 // the elimination window lives in shared memory (WS) or, for very wide bands, in a global scratch buffer

@@ -67,7 +67,9 @@ def _gait_flags(F, dt, rng, dense):
 
 
 def make_problem(seed: int, n_frames: int = 120, n_ee: int = 2, fps: float = 30.0, dense: bool = False,
-                 noise: float = 0.005) -> PhysProblem:
+                 noise: float = 0.005, toe_flags=None) -> PhysProblem:
+    """`toe_flags` (2 x F, 0/1; e.g. columns L toe / R toe of a `foot_contacts.npy`) replaces the gait clock: the
+    synthetic feet then follow the given contact pattern (every foot needs at least one stance frame)."""
     rng = np.random.default_rng(seed)
     F, dt = n_frames, 1.0 / fps
     t = np.arange(F) * dt
@@ -93,7 +95,8 @@ def make_problem(seed: int, n_frames: int = 120, n_ee: int = 2, fps: float = 30.
     per = np.array([T_sway, T_sway / 2, T_sway]) * rng.uniform(0.9, 1.1, 3)
     ang = amp[None, :] * np.sin(2 * np.pi * t[:, None] / per[None, :] + ph[None, :])
 
-    toe_flags = _gait_flags(F, dt, rng, dense)
+    gait = _gait_flags(F, dt, rng, dense)      # always drawn, so that the rest of the stream does not depend on the override
+    toe_flags = gait if toe_flags is None else np.asarray(toe_flags, dtype=np.int64).reshape(2, F)
     d_foot = 0.17
     side = [0.09, -0.09]  # left +y, right -y
     dirx = np.array([1.0, 0.0, 0.0])

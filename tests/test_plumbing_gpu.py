@@ -1,0 +1,69 @@
+"""BASELINE.json configs[0] ("single clip: contact detect + phys_optim", plumbing): the two drop-in scripts chained
+through the reference's own files -- openpose_result/*.json -> foot_contacts.npy -> contact_info.txt (+ the three
+other phys_optim inputs) -> sol_out_*.txt / success_log.txt.  The step in between (towr_utils.prepare_input: BVH
+FK, inertia, label clean-up) is not built, so the motion side of the clip is synthetic and a
+5-frame majority filter stands in for the label clean-up."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def test_single_clip_files_end_to_end(chd, tmp_path):
+    from make_contact_golden import contact_weights, synth_keypoints
+    F, fps = 101, 24.0                                   # dance2's shape
+    data, out = tmp_path / "data", tmp_path / "out"
+    op = data / "clip" / "openpose_result"
+    os.makedirs(op)
+    kp = synth_keypoints(7, F)
+    for i in range(F):
+        people = [] if i == 40 else [{"pose_keypoints_2d": kp[i].reshape(-1).tolist()}]   # one frame without a detection
+        with open(op / ("clip_%012d_keypoints.json" % i), "w") as f:
+            json.dump({"version": 1.2, "people": people}, f)
+    np.savez(tmp_path / "weights.npz", **contact_weights(0))
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "detect_contacts.py"), "--data", str(data), "--out", str(out),
+                           "--weights-path", str(tmp_path / "weights.npz"), "--full-video", "--save-contacts", "--real-data",
+                           "--copy-into-data"])
+    labels = np.load(data / "clip" / "foot_contacts.npy")
+    assert labels.shape == (F, 4) and labels.dtype == np.int64 and set(np.unique(labels)) <= {0, 1}
+    np.testing.assert_array_equal(labels, np.load(out / "contact_results" / "clip" / "foot_contacts.npy"))
+
+    # label clean-up stand-in: 5-frame majority vote on the toe columns (L toe = 1, R toe = 3), a stance at both ends
+    toe = labels[:, [1, 3]].T.astype(np.int64)
+    pad = np.pad(toe, ((0, 0), (2, 2)), mode="edge")
+    toe = (sum(pad[:, k:k + F] for k in range(5)) >= 3).astype(np.int64)
+    toe[:, :3], toe[:, -3:] = 1, 1
+    p = chd.synth.make_problem(7, n_frames=F, n_ee=2, fps=fps, toe_flags=toe)
+    ind, outd = tmp_path / "phys_optim_in_ybot", tmp_path / "phys_optim_out_ybot"
+    os.makedirs(outd)
+    chd.io_formats.write_phys_inputs(p, str(ind))
+    # contact_info.txt carries exactly the phases of the detected labels (towr_utils.py:435-449)
+    for e in range(2):
+        np.testing.assert_allclose(p.ee_durations[e], chd.io_formats.find_contact_durations(list(toe[e]), 1.0 / fps))
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "phys_optim.py"), "--in_dir", str(ind), "--nframes", str(F),
+                           "--out_dir", str(outd), "--n_ee", "2"])
+    sols = {}
+    for name in ("sol_out_no_dynamics.txt", "sol_out_dynamics.txt", "sol_out_durations.txt"):
+        r = chd.io_formats.read_solution(str(outd / name))
+        assert r["num_frames"] == F and r["num_feet"] == 2
+        assert all(np.isfinite(np.asarray(v, float)).all() for v in r.values() if isinstance(v, np.ndarray))
+        sols[name] = r
+    log = open(outd / "success_log.txt").read().split()
+    assert log[0] == "dynamics" and log[2] == "durations" and log[1] in "01" and log[3] in "01"
+    # the written contact flags are the detected phases sampled at the frame times (boundary frames may go either way)
+    flags = sols["sol_out_durations.txt"]["foot_contact"].T        # (F, 2)
+    interior = np.ones(F, bool)
+    for e in range(2):
+        ch = np.flatnonzero(np.diff(toe[e]) != 0)
+        interior[ch] = False
+        interior[ch + 1] = False
+    interior[-1] = False
+    np.testing.assert_array_equal(flags[interior], toe.T[interior])
