@@ -473,8 +473,9 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       const bool compact = Gm <= 32;
       const int np_loop = compact ? na * (na + 1) / 2 : npairs;
       if (!WS) {
-        // window in global (L2) memory: every tile access is a long-latency load, so each warp collects up to four
-        // target tiles, issues all their loads, and only then runs the tensor-core updates and the stores
+        // window in global (L2) memory: each warp collects up to four target tiles, issues all their loads, and only
+        // then runs the tensor-core updates and the stores.  (With the window in shared memory the simple loop below
+        // is faster: measured 707 vs 820 ms of KKT time per benchmark step.)
         const int r8 = (lane >> 2) * 8 + 2 * (lane & 3);
         int p = warp - 1;
         while (p < np_loop) {
