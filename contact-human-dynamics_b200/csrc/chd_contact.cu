@@ -3,129 +3,173 @@
 // Replaces, for inference, src/contact_learning/test.py:51-152 (val_full_video) +
 // src/contact_learning/models/openpose_only.py:29-78 + the window construction of
 // src/contact_learning/data/real_video_dataset.py:206-276:
-//   chd_k_contact_mlp  : gathers the 9-frame x 13-joint x (x,y,conf) windows straight from the per-frame keypoints
-//                        (root-relative as the dataset does it, fp64 subtraction then fp32), and runs the whole MLP
-//                        351-1024-512-128-32-20 (Linear + eval BatchNorm + ReLU) with activations in shared memory
-//   chd_k_contact_vote : sigmoid > 0.5, 5-vote aggregation, edge thresholds, 2-frame padding, int64 labels
-// fp32 FFMA with fp32 accumulation (no tf32/bf16): the labels must match the reference's fp32 forward bit for bit
-// away from the logit-0 boundary (SURVEY 8(a)-D note).
+//   chd_k_contact_gather : the 9-frame x 13-joint x (x,y,conf) windows straight from the per-frame keypoints
+//                          (root-relative as the dataset does it, fp64 subtraction then fp32)
+//   chd_k_contact_gemm   : one Linear + eval BatchNorm + ReLU layer over a slab of windows, 128x128x16 tiles,
+//                          8x8 outputs per thread, double-buffered shared-memory tiles (layers 351-1024-512-128)
+//   chd_k_contact_tail   : the two small layers 128-32-20
+//   chd_k_contact_vote   : sigmoid > 0.5, 5-vote aggregation, edge thresholds, 2-frame padding, int64 labels
+// Windows are processed in slabs of 16384 so that the activations of a slab (132 MB) stay in the 126 MB L2 / HBM
+// working set instead of shared memory; every output is one fp32 accumulator summed over k in ascending order
+// (fmaf), the same arithmetic as a plain loop.  fp32 FFMA, no tf32/bf16: the integer labels must match the
+// reference's fp32 forward away from the logit-0 boundary (SURVEY 8(a)-D note; tcgen05 has no fp32 kind).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <vector>
 
 #include "../../include/chd.h"
 
-#define CT_TM 32        // windows per CTA
-#define CT_THREADS 256
 #define CT_WIN 9
 #define CT_PRED 5
 #define CT_J 13
 #define CT_IN 351
+#define CT_K0 352        // first layer's K padded to the tile depth
+#define CT_SLAB 16384    // windows per slab
+#define GM 128
+#define GN 128
+#define GK 16
 
 static __device__ __constant__ int c_lower_joints[CT_J] = {8, 9, 10, 11, 12, 13, 14, 19, 20, 21, 22, 23, 24};  // openpose_dataset.py:38
 
 struct ContactDev {
-  const float* W[5];   // [in][out] (transposed on the host)
+  const float* W[5];   // [in][out] (transposed on the host; layer 0 has CT_K0 rows, the last one zero)
   const float* b[5];
   const float* bn_scale[4];  // gamma / sqrt(var + eps)
   const float* bn_mean[4];
   const float* bn_beta[4];
 };
 
-// out[m][n] = relu( bn( in[m][:] . W[:][n] + b[n] ) ) for the CTA's CT_TM windows.
-// warp w: rows (w & 3)*8 .. +7, column half (w >> 2); per pass 4 columns per lane strided by 32 (coalesced weights).
-template <bool BN_RELU>
-__device__ __forceinline__ void contact_layer(const float* __restrict__ in, int Kp, int K, const float* __restrict__ W,
-                                              const float* __restrict__ bias, const float* __restrict__ scale,
-                                              const float* __restrict__ mean, const float* __restrict__ beta, int N,
-                                              float* __restrict__ out, int Np) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mg = warp & 3, nh = warp >> 2;
-  const float* a0 = in + (size_t)(mg * 8) * Kp;
-  for (int n0 = nh * 128; n0 < N; n0 += 256) {
-    float acc[8][4];
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
-    int nc[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) nc[j] = n0 + lane + 32 * j;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      float wv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wv[j] = nc[j] < N ? __ldg(W + (size_t)k * N + nc[j]) : 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float a = a0[r * Kp + k];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[r][j] = fmaf(a, wv[j], acc[r][j]);
-      }
+// frames: [V][Fmax][25][3] fp64 (scaled, gap-interpolated, normalised keypoints) -> A0 [Mp][CT_K0] fp32 for the
+// windows g0 .. g0+Mp-1 (rows past the last window and column 351 are zero), real_video_dataset.py:240-252
+__global__ void __launch_bounds__(256) chd_k_contact_gather(const double* __restrict__ frames, int V, int Fmax, int g0, int Mp,
+                                                            float* __restrict__ A0) {
+  const int Wn = Fmax - (CT_WIN - 1), total = V * Wn;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Mp * CT_K0) return;
+  const int m = (int)(idx / CT_K0), k = (int)(idx % CT_K0), g = g0 + m;
+  float val = 0.f;
+  if (g < total && k < CT_IN) {
+    const int v = g / Wn, w = g % Wn;
+    const int f = k / (CT_J * 3), rem = k % (CT_J * 3), j = rem / 3, c = rem % 3;
+    const int joint = c_lower_joints[j];
+    const double* fr = frames + (((size_t)v * Fmax + w + f) * 25 + joint) * 3;
+    if (c == 2) {
+      val = (float)fr[2];
+    } else {
+      const double root = frames[(((size_t)v * Fmax + w + CT_WIN / 2) * 25 + 8) * 3 + c];
+      val = (f == CT_WIN / 2 && joint == 8) ? (float)root : (float)(fr[c] - root);
     }
+  }
+  A0[idx] = val;
+}
+
+// C[Mp][N] = relu(bn(A[Mp][K] W[K][N] + bias)); Mp % 128 == 0, N % 128 == 0, K % 16 == 0.
+// 256 threads; thread (ty, tx) owns rows {4ty..4ty+3, 64+4ty..} x columns {4tx..4tx+3, 64+4tx..}.
+__global__ void __launch_bounds__(256) chd_k_contact_gemm(const float* __restrict__ A, const float* __restrict__ W, int K, int N,
+                                                          const float* __restrict__ bias, const float* __restrict__ scale,
+                                                          const float* __restrict__ mean, const float* __restrict__ beta,
+                                                          float* __restrict__ C) {
+  __shared__ __align__(16) float As[2][GK][GM];   // transposed A tile
+  __shared__ __align__(16) float Bs[2][GK][GN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  // global -> register staging: A tile 128 x 16 = 512 float4 (2 per thread), B tile 16 x 128 = 512 float4
+  const int ar = tid >> 2, ac = (tid & 3) * 4;          // A rows ar, ar + 64; k offset ac
+  const int br = tid >> 5, bc = (tid & 31) * 4;         // B rows br, br + 8; column offset bc
+  const float* Ap = A + (size_t)(m0 + ar) * K + ac;
+  const float* Bp = W + (size_t)br * N + n0 + bc;
+  float4 ra0, ra1, rb0, rb1;
+  auto gload = [&](int k0) {
+    ra0 = *reinterpret_cast<const float4*>(Ap + k0);
+    ra1 = *reinterpret_cast<const float4*>(Ap + (size_t)64 * K + k0);
+    rb0 = __ldg(reinterpret_cast<const float4*>(Bp + (size_t)k0 * N));
+    rb1 = __ldg(reinterpret_cast<const float4*>(Bp + (size_t)(k0 + 8) * N));
+  };
+  auto sstore = [&](int buf) {
+    As[buf][ac + 0][ar] = ra0.x, As[buf][ac + 1][ar] = ra0.y, As[buf][ac + 2][ar] = ra0.z, As[buf][ac + 3][ar] = ra0.w;
+    As[buf][ac + 0][ar + 64] = ra1.x, As[buf][ac + 1][ar + 64] = ra1.y, As[buf][ac + 2][ar + 64] = ra1.z, As[buf][ac + 3][ar + 64] = ra1.w;
+    *reinterpret_cast<float4*>(&Bs[buf][br][bc]) = rb0;
+    *reinterpret_cast<float4*>(&Bs[buf][br + 8][bc]) = rb1;
+  };
+  float acc[8][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (nc[j] >= N) continue;
-      const float bj = bias[nc[j]];
-      float sc = 1.f, mu = 0.f, be = 0.f;
-      if (BN_RELU) sc = scale[nc[j]], mu = mean[nc[j]], be = beta[nc[j]];
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        float y = acc[r][j] + bj;
-        if (BN_RELU) {
-          y = (y - mu) * sc + be;
-          y = fmaxf(y, 0.f);
-        }
-        out[(size_t)(mg * 8 + r) * Np + nc[j]] = y;
-      }
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += GK, buf ^= 1) {
+    const bool more = k0 + GK < K;
+    if (more) gload(k0 + GK);
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) sstore(buf ^ 1);
+    __syncthreads();
+  }
+  // epilogue: bias, eval BatchNorm as (y - mean) * scale + beta, ReLU
+#pragma unroll
+  for (int jh = 0; jh < 2; ++jh) {
+    const int n = n0 + jh * 64 + tx * 4;
+    const float4 bj = *reinterpret_cast<const float4*>(bias + n), sc = *reinterpret_cast<const float4*>(scale + n);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + n), be = *reinterpret_cast<const float4*>(beta + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+      float4 y;
+      y.x = fmaxf((acc[i][jh * 4 + 0] + bj.x - mu.x) * sc.x + be.x, 0.f);
+      y.y = fmaxf((acc[i][jh * 4 + 1] + bj.y - mu.y) * sc.y + be.y, 0.f);
+      y.z = fmaxf((acc[i][jh * 4 + 2] + bj.z - mu.z) * sc.z + be.z, 0.f);
+      y.w = fmaxf((acc[i][jh * 4 + 3] + bj.w - mu.w) * sc.w + be.w, 0.f);
+      *reinterpret_cast<float4*>(C + (size_t)m * N + n) = y;
     }
   }
 }
 
-// frames: [V][Fmax][25][3] fp64 (scaled, gap-interpolated, normalised keypoints); logits: [V*Wn][20]
-__global__ void __launch_bounds__(CT_THREADS) chd_k_contact_mlp(ContactDev net, const double* __restrict__ frames, int V, int Fmax,
-                                                                float* __restrict__ logits) {
-  extern __shared__ float smf[];
-  float* bufA = smf;                 // 32 x 1024
-  float* bufB = smf + CT_TM * 1024;  // 32 x 512
-  const int Wn = Fmax - (CT_WIN - 1);
-  const int total = V * Wn;
-  const int g0 = blockIdx.x * CT_TM;
-  // gather windows into bufB [32][352] (real_video_dataset.py:240-252)
-  for (int idx = threadIdx.x; idx < CT_TM * 352; idx += blockDim.x) {
-    const int m = idx / 352, k = idx % 352;
-    float val = 0.f;
-    const int g = g0 + m;
-    if (g < total && k < CT_IN) {
-      const int v = g / Wn, w = g % Wn;
-      const int f = k / (CT_J * 3), rem = k % (CT_J * 3), j = rem / 3, c = rem % 3;
-      const int joint = c_lower_joints[j];
-      const double* fr = frames + (((size_t)v * Fmax + w + f) * 25 + joint) * 3;
-      if (c == 2) {
-        val = (float)fr[2];
-      } else {
-        const double root = frames[(((size_t)v * Fmax + w + CT_WIN / 2) * 25 + 8) * 3 + c];
-        val = (f == CT_WIN / 2 && joint == 8) ? (float)root : (float)(fr[c] - root);
-      }
+// layers 128 -> 32 (BN + ReLU) -> 20 for 32 windows per CTA; logits [total][20]
+__global__ void __launch_bounds__(256) chd_k_contact_tail(ContactDev net, const float* __restrict__ A3, int g0, int total,
+                                                          float* __restrict__ logits) {
+  __shared__ float sA[32][129];
+  __shared__ float sW3[128 * 32];
+  __shared__ float sH[32][33];
+  __shared__ float sW4[32 * 20];
+  const int tid = threadIdx.x, m0 = blockIdx.x * 32;
+  for (int i = tid; i < 32 * 128; i += 256) sA[i >> 7][i & 127] = A3[(size_t)(m0 + (i >> 7)) * 128 + (i & 127)];
+  for (int i = tid; i < 128 * 32; i += 256) sW3[i] = net.W[3][i];
+  for (int i = tid; i < 32 * 20; i += 256) sW4[i] = net.W[4][i];
+  __syncthreads();
+  {
+    const int n = tid & 31;
+    const float bj = net.b[3][n], sc = net.bn_scale[3][n], mu = net.bn_mean[3][n], be = net.bn_beta[3][n];
+    for (int m = tid >> 5; m < 32; m += 8) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < 128; ++k) acc = fmaf(sA[m][k], sW3[k * 32 + n], acc);
+      sH[m][n] = fmaxf((acc + bj - mu) * sc + be, 0.f);
     }
-    bufB[idx] = val;
   }
   __syncthreads();
-  contact_layer<true>(bufB, 352, CT_IN, net.W[0], net.b[0], net.bn_scale[0], net.bn_mean[0], net.bn_beta[0], 1024, bufA, 1024);
-  __syncthreads();
-  contact_layer<true>(bufA, 1024, 1024, net.W[1], net.b[1], net.bn_scale[1], net.bn_mean[1], net.bn_beta[1], 512, bufB, 512);
-  __syncthreads();
-  contact_layer<true>(bufB, 512, 512, net.W[2], net.b[2], net.bn_scale[2], net.bn_mean[2], net.bn_beta[2], 128, bufA, 128);
-  __syncthreads();
-  contact_layer<true>(bufA, 128, 128, net.W[3], net.b[3], net.bn_scale[3], net.bn_mean[3], net.bn_beta[3], 32, bufB, 32);
-  __syncthreads();
-  contact_layer<false>(bufB, 32, 32, net.W[4], net.b[4], nullptr, nullptr, nullptr, 20, bufA, 20);
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < CT_TM * 20; idx += blockDim.x) {
-    const int g = g0 + idx / 20;
-    if (g < total) logits[(size_t)g * 20 + idx % 20] = bufA[idx];
+  for (int i = tid; i < 32 * 20; i += 256) {
+    const int m = i / 20, n = i % 20, g = g0 + m0 + m;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = fmaf(sH[m][k], sW4[k * 20 + n], acc);
+    if (g < total) logits[(size_t)g * 20 + n] = acc + net.b[4][n];
   }
 }
 
@@ -165,6 +209,8 @@ struct chd_contact_net {
   ContactDev dev;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  float* ws = nullptr;     // activation workspace of one slab: A0 [Mp][352] | A1 [Mp][1024] | A2 [Mp][512] | A3 [Mp][128]
+  int ws_rows = 0;
 };
 
 #define CT_CUDA(x)                                                                           \
@@ -197,7 +243,7 @@ int chd_contact_create(const float* weights, const float* biases, const float* b
   const float* q = bn;
   for (int l = 0; l < 5; ++l) {
     const int in = dims[l], o = dims[l + 1];
-    std::vector<float> wt((size_t)in * o), bb(b, b + o);
+    std::vector<float> wt((size_t)(l == 0 ? CT_K0 : in) * o, 0.f), bb(b, b + o);
     for (int i = 0; i < o; ++i)
       for (int k = 0; k < in; ++k) wt[(size_t)k * o + i] = w[(size_t)i * in + k];   // torch [out][in] -> [in][out]
     int rc;
@@ -216,7 +262,6 @@ int chd_contact_create(const float* weights, const float* biases, const float* b
       q += 4 * o;
     }
   }
-  CT_CUDA(cudaFuncSetAttribute(chd_k_contact_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CT_TM * (1024 + 512) * sizeof(float))));
   *out = net;
   return 0;
 }
@@ -224,6 +269,7 @@ int chd_contact_create(const float* weights, const float* biases, const float* b
 void chd_contact_destroy(chd_contact_net* net) {
   if (!net) return;
   for (void* p : net->allocs) cudaFree(p);
+  if (net->ws) cudaFree(net->ws);
   if (net->stream) cudaStreamDestroy(net->stream);
   delete net;
 }
@@ -235,9 +281,29 @@ int chd_contact_forward_device(chd_contact_net* net, const double* frames_dev, i
   const int Wn = Fmax - (CT_WIN - 1), total = V * Wn;
   const float big = 3.4e38f;
   CT_CUDA(cudaMemcpyAsync(min_abs_dev, &big, sizeof(float), cudaMemcpyHostToDevice, s));
-  chd_k_contact_mlp<<<(total + CT_TM - 1) / CT_TM, CT_THREADS, CT_TM * (1024 + 512) * sizeof(float), s>>>(net->dev, frames_dev, V, Fmax, logits_dev);
+  const int rows = std::min(CT_SLAB, (total + GM - 1) / GM * GM);
+  if (rows > net->ws_rows) {
+    if (net->ws) cudaFree(net->ws);
+    net->ws = nullptr, net->ws_rows = 0;
+    CT_CUDA(cudaMalloc((void**)&net->ws, (size_t)rows * (CT_K0 + 1024 + 512 + 128) * sizeof(float)));
+    net->ws_rows = rows;
+  }
+  float* A0 = net->ws;
+  float* A1 = A0 + (size_t)net->ws_rows * CT_K0;
+  float* A2 = A1 + (size_t)net->ws_rows * 1024;
+  float* A3 = A2 + (size_t)net->ws_rows * 512;
+  const ContactDev& d = net->dev;
+  for (int g0 = 0; g0 < total; g0 += CT_SLAB) {
+    const int Mp = (std::min(CT_SLAB, total - g0) + GM - 1) / GM * GM;
+    chd_k_contact_gather<<<(unsigned)(((size_t)Mp * CT_K0 + 255) / 256), 256, 0, s>>>(frames_dev, V, Fmax, g0, Mp, A0);
+    chd_k_contact_gemm<<<dim3(1024 / GN, Mp / GM), 256, 0, s>>>(A0, d.W[0], CT_K0, 1024, d.b[0], d.bn_scale[0], d.bn_mean[0], d.bn_beta[0], A1);
+    chd_k_contact_gemm<<<dim3(512 / GN, Mp / GM), 256, 0, s>>>(A1, d.W[1], 1024, 512, d.b[1], d.bn_scale[1], d.bn_mean[1], d.bn_beta[1], A2);
+    chd_k_contact_gemm<<<dim3(128 / GN, Mp / GM), 256, 0, s>>>(A2, d.W[2], 512, 128, d.b[2], d.bn_scale[2], d.bn_mean[2], d.bn_beta[2], A3);
+    chd_k_contact_tail<<<Mp / 32, 256, 0, s>>>(d, A3, g0, total, logits_dev);
+    net->launches += 5;
+  }
   chd_k_contact_vote<<<(V * Fmax * 4 + 255) / 256, 256, 0, s>>>(logits_dev, V, Fmax, seq_lens_dev, (long long*)labels_dev, min_abs_dev);
-  net->launches += 2;
+  net->launches += 1;
   CT_CUDA(cudaGetLastError());
   return 0;
 }
