@@ -10,6 +10,13 @@
 //
 // PARITY UNPINNED: the reference's own solver stack (IPOPT + MA57 + L-BFGS) cannot be built offline; this
 // oracle pins the CUDA solver to the same algorithm run on the CPU, not to IPOPT iterates.
+// Experimental switches (environment variables, all off by default; the parity tests use the defaults):
+//   CHD_EXACT=1      exact bilinear momentum curvature of the dynamics rows + inertia control (negative pivots of the
+//                    band LDL^T must equal the number of equality rows, otherwise delta_w *= CHD_DW_INERTIA (8))
+//   CHD_DW_MIN, CHD_DW_DEC   floor / decay factor of the Levenberg-Marquardt regularisation (1e-8, 3)
+//   CHD_MU_MIN, CHD_MU_SF    barrier floor (default min(tol, compl_inf_tol) / 11; IPOPT's own default is 1e-11)
+//   CHD_NDUR, CHD_DREG       proximal term on the last CHD_NDUR variables (stage-3 duration variables)
+// They document the convergence studies summarised in DESIGN.md section 4.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -59,7 +66,7 @@ struct Triplets {
 
 // symmetric arrowhead matrix: band part (row-major, row i holds columns i-w..i) + dense border rows
 struct Arrow {
-  int Na = 0, nb = 0, w = 0;
+  int Na = 0, nb = 0, w = 0, n_neg = 0;   // n_neg: negative pivots of the last factorisation (band part)
   std::vector<double> band, bord, corn, rhs;  // band[i*(w+1) + (w-(i-j))], bord[b*Na + j], corn[b*nb + b2] (lower), rhs[Na+nb]
   void init(int Na_, int nb_, int w_) {
     Na = Na_, nb = nb_, w = w_;
@@ -79,8 +86,10 @@ struct Arrow {
     const int W = w + 1;
     auto A = [&](int i, int j) -> double& { return band[(size_t)i * W + (w - (i - j))]; };
     std::vector<double> z(rhs);
+    n_neg = 0;
     for (int k = 0; k < Na; ++k) {
       const double d = A(k, k);
+      n_neg += d < 0.0;
       if (!(std::fabs(d) > 1e-300) || !std::isfinite(d)) { if (getenv("CHDO_DEBUG")) fprintf(stderr, "band pivot %d = %g\n", k, d); return false; }
       const int lim = std::min(w, Na - 1 - k);
       // column k of L in the band
@@ -136,7 +145,7 @@ struct Solver {
   Opts o;
   int n = 0, m = 0;
   std::vector<double> xlo, xhi, cl, cu;
-  std::vector<char> fixed, eq, hasL, hasU, dist_row;
+  std::vector<char> fixed, eq, hasL, hasU, dist_row, dyn_row;
   std::vector<int> vk, rk;  // KKT ordering
   int Na = 0, nb = 0, w = 0;
   // CSR Jacobian
@@ -224,7 +233,7 @@ struct Solver {
       if (xlo[i] == xhi[i]) fixed[i] = 1, x[i] = xlo[i];
     cl.assign(m, 0), cu.assign(m, 0);
     chdo_con_bounds(h, cl.data(), cu.data());
-    eq.assign(m, 0), hasL.assign(m, 0), hasU.assign(m, 0), dist_row.assign(m, 0);
+    eq.assign(m, 0), hasL.assign(m, 0), hasU.assign(m, 0), dist_row.assign(m, 0), dyn_row.assign(m, 0);
     for (int r = 0; r < m; ++r) {
       eq[r] = cl[r] == cu[r];
       hasL[r] = !eq[r] && cl[r] > -kInf;
@@ -237,6 +246,8 @@ struct Solver {
         int rows = chdo_constraint_set_rows(h, i);
         if (nm.rfind("leg-length", 0) == 0 || nm.rfind("ee-dist", 0) == 0)
           for (int r = off; r < off + rows; ++r) dist_row[r] = 1;
+        if (nm == "dynamic")
+          for (int r = off; r < off + rows; ++r) dyn_row[r] = 1;
         off += rows;
       }
     }
@@ -288,12 +299,20 @@ struct Solver {
       n_bounds += hasL[r] + hasU[r];
     }
     double mu = o.mu_init, delta_w = o.delta_w0, mu_filter = -1.0, theta_max = 0, theta_min = 0;
-    const double mu_min = std::min(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
+    double mu_min = getenv("CHD_MU_MIN") ? atof(getenv("CHD_MU_MIN")) : std::min(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
+    if (getenv("CHD_MU_SF")) mu_min = std::min(o.tol, o.compl_inf_tol * sf) / (o.kappa_eps + 1.0);   // the unscaled complementarity test must be reachable
+    if (verbose) printf("sf %.4f mu_min %.3e\n", sf, mu_min);
     std::vector<std::pair<double, double>> filt;
     int status = -1, it = 0, ls_fail = 0;
     double E0 = 0, violu = 0, dual_u = 0, compl_u = 0;
     std::vector<double> rx(n), dx(n), ds(m), dy(m), dzL(m), dzU(m), sol, ypos(m), xt(n), ct;
     Arrow K;
+    const bool exact_curv = getenv("CHD_EXACT") != nullptr;
+    const double dw_inertia = getenv("CHD_DW_INERTIA") ? atof(getenv("CHD_DW_INERTIA")) : 8.0;
+    int n_eq_rows = 0, n_inertia = 0;
+    for (int r = 0; r < m; ++r) n_eq_rows += eq[r] && rk[r] >= 0 && rk[r] < Na;
+    if (getenv("CHD_DW_MIN")) o.dw_min = atof(getenv("CHD_DW_MIN"));
+    if (getenv("CHD_DW_DEC")) o.dw_dec = atof(getenv("CHD_DW_DEC"));
     const int exp_ndur = getenv("CHD_NDUR") ? atoi(getenv("CHD_NDUR")) : 0;
     const double exp_dreg = getenv("CHD_DREG") ? atof(getenv("CHD_DREG")) : 0.0;
     for (it = 0;; ++it) {
@@ -353,6 +372,9 @@ struct Solver {
       if (mu != mu_filter) filt.clear(), mu_filter = mu;
       // ---- condensed KKT ----
       for (int r = 0; r < m; ++r) ypos[r] = (dist_row[r] && sc[r] * y[r] > 1e-8) ? sc[r] * y[r] : 0.0;  // CHD_CURV_MIN
+      if (exact_curv)
+        for (int r = 0; r < m; ++r)
+          if (dyn_row[r]) ypos[r] = sc[r] * y[r];   // exact bilinear momentum terms (indefinite: inertia control below)
       Triplets W1 = hess(true, nullptr), W2 = hess(false, ypos.data());
       w = bandwidth(W1, W2);
       K.init(Na, nb, w);
@@ -395,6 +417,14 @@ struct Solver {
         }
       }
       const bool ok = K.solve(sol);
+      if (ok && exact_curv && K.n_neg != n_eq_rows) {
+        // wrong inertia: the step would not be a descent direction for the barrier problem; stiffen and retry
+        delta_w = std::min(std::max(delta_w * dw_inertia, 1e-8), o.dw_max * 10);
+        n_inertia++;
+        if (verbose > 1) printf("      inertia %d != %d -> dw %.1e\n", K.n_neg, n_eq_rows, delta_w);
+        if (delta_w > o.dw_max) { status = -2; break; }
+        continue;
+      }
       if (!ok) {
         delta_w = std::min(std::max(delta_w * 100.0, 1e-4), o.dw_max * 10);
         ls_fail++;
