@@ -2,6 +2,8 @@
 #include "chd_layout.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -473,9 +475,20 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
 
 int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys_weights& wt, ChdHostBatch& hb) {
   std::vector<SeqBuild> sbs(batch);
-  for (int i = 0; i < batch; ++i) {
-    int rc = build_sequence(problems[i], sbs[i]);
-    if (rc) return rc;
+  {
+    // sequences are independent: build their tables on the host cores in parallel (end-to-end latency of a batch)
+    const int nth = std::max(1, std::min<int>({batch, 16, (int)std::thread::hardware_concurrency()}));
+    std::vector<int> rcs(batch, 0);
+    std::atomic<int> next(0);
+    auto work = [&]() {
+      for (int i = next.fetch_add(1); i < batch; i = next.fetch_add(1)) rcs[i] = build_sequence(problems[i], sbs[i]);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nth; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    for (int i = 0; i < batch; ++i)
+      if (rcs[i]) return rcs[i];
   }
   hb.B = batch;
   auto up = [](int& a, int b) { a = std::max(a, b); };
