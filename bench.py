@@ -232,7 +232,11 @@ def main():
         # dominant kernel: chd_k_kkt.  Algorithmic bytes per launch: per sequence
         # 8*(nslots [J] + 2n [grad, dx] + 12m [row state in/out]); the band itself is scratch.
         sz = batch.sizes.astype(np.int64)
-        running_launch_bytes = float((8 * (sz[:, 2] + 2 * sz[:, 0] + 12 * sz[:, 1])).sum())
+        # every sequence walks through the schedule at its own pace, so a launch factorises only the sequences that are
+        # still iterating: units per launch = (sum of iterations over sequences and stages) / launches
+        seq_iters = np.asarray(last[1])[[0, 1, 2, 3, 5]].sum(axis=0).astype(np.float64)      # per sequence
+        act = seq_iters / max(kt["kkt"][1], 1)                                            # share of the launches a sequence is active in
+        running_launch_bytes = float((8 * (sz[:, 2] + 2 * sz[:, 0] + 12 * sz[:, 1]) * act).sum())
         kkt_ms, kkt_n = kt["kkt"]
         eval_ms, eval_n = kt["eval"]
         ach = running_launch_bytes / (kkt_ms / max(kkt_n, 1) * 1e-3) / 1e9 if kkt_n else 0.0
@@ -241,10 +245,15 @@ def main():
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kkt_ncu.json")))
-            traffic = prof["dram_bytes_per_sequence_per_launch"] * B   # ncu --set full capture (profiles/r1_kkt_ncu_summary.md), per launch
+            traffic = prof["dram_bytes_per_sequence_per_launch"] * float(act.sum())   # ncu --set full capture (profiles/r1_kkt_ncu_summary.md), per launch
         except Exception:
             pass
-        kkt_flops = float((sz[:, 3] * (sz[:, 5].astype(np.float64) ** 2 + 2.0 * sz[:, 5] * (sz[:, 4] + 1) + (sz[:, 4] + 1.0) ** 2)).sum())
+        kkt_flops = float((act * sz[:, 3] * (sz[:, 5].astype(np.float64) ** 2 + 2.0 * sz[:, 5] * (sz[:, 4] + 1) + (sz[:, 4] + 1.0) ** 2)).sum())
+        kkt_gflops = kkt_flops * 2 / (kkt_ms / max(kkt_n, 1) * 1e-3) / 1e9
+        try:
+            dfma_peak, dmma_peak = chd.phys.measure_fp64_peak()
+        except Exception:
+            dfma_peak = dmma_peak = None
         line = {
             "metric": "optimised frames/sec (batched phys-optim)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
@@ -260,7 +269,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "chd_k_kkt", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": running_launch_bytes, "peak_source": peak_src,
                          "note": "fp64-FMA / latency bound kernel (DESIGN.md); HBM fraction reported as the contract asks",
-                         "ms_per_launch": kkt_ms / max(kkt_n, 1), "fp64_gflops": kkt_flops * 2 / (kkt_ms / max(kkt_n, 1) * 1e-3) / 1e9},
+                         "ms_per_launch": kkt_ms / max(kkt_n, 1), "active_sequences_per_launch": float(act.sum()), "fp64_gflops": kkt_gflops},
+            "roofline_fp64": {"bound": "fp64 tensor core (DMMA m8n8k4)", "kernel": "chd_k_kkt", "achieved": kkt_gflops, "unit": "GFLOP/s",
+                              "peak": dmma_peak, "peak_dfma": dfma_peak, "frac": (kkt_gflops / dmma_peak) if dmma_peak else None,
+                              "peak_source": "chd_measure_fp64_peak, measured in this run (all SMs)",
+                              "note": "band-dense LDL^T flop count (2*Na*(w+nb+1)^2 per active sequence); one CTA per sequence, so at most "
+                                      "active_sequences_per_launch of the 148 SMs work"},
             "kernels": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
             "roofline_eval": {"bound": "hbm", "kernel": "chd_k_eval", "achieved": eval_ach, "peak": hbm_peak, "unit": "GB/s",
                               "frac": eval_ach / hbm_peak},

@@ -16,6 +16,7 @@ __global__ void chd_k_init(ChdDev D);
 __global__ void chd_k_kkt(ChdDev D);
 __global__ void chd_k_kkt_gwin(ChdDev D);
 __global__ void chd_k_kcopy(ChdDev D);
+__global__ void chd_k_fp64_peak(int mode, int iters, double* sink);
 __global__ void chd_k_hess_base(ChdDev D);
 __global__ void chd_k_linesearch(ChdDev D);
 __global__ void chd_k_sample(ChdDev D, double* out, int* frames_out);
@@ -187,6 +188,36 @@ int run_schedule(chd_phys_batch* b) {
 extern "C" {
 
 const char* chd_version(void) { return "libchd 0.1 (sm_100a)"; }
+
+int chd_measure_fp64_peak(double* dfma_gflops, double* dmma_gflops) {
+  int dev = 0, sms = 0;
+  CHD_CUDA(cudaGetDevice(&dev));
+  CHD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  CHD_CUDA(cudaMalloc((void**)&sink, sizeof(double) * 1024));
+  cudaEvent_t e0, e1;
+  CHD_CUDA(cudaEventCreate(&e0));
+  CHD_CUDA(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  for (int mode = 0; mode < 2; ++mode) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      CHD_CUDA(cudaEventRecord(e0));
+      chd_k_fp64_peak<<<blocks, threads>>>(mode, iters, sink);
+      CHD_CUDA(cudaEventRecord(e1));
+      CHD_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      CHD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    // mode 0: 8 independent FMA chains per thread; mode 1: 4 independent m8n8k4 accumulators per warp (512 flop each)
+    const double flop = mode == 0 ? (double)blocks * threads * iters * 8 * 2 : (double)blocks * (threads / 32) * iters * 4 * 512;
+    double* out = mode == 0 ? dfma_gflops : dmma_gflops;
+    if (out) *out = flop / (best * 1e-3) / 1e9;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(sink);
+  return 0;
+}
 
 int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const chd_phys_weights* weights, int32_t device,
                           chd_phys_batch** out) {

@@ -734,6 +734,33 @@ __global__ void __launch_bounds__(256) chd_k_kcopy(ChdDev D) {
   for (; i < hi; i += nt) dst[i] = src[i];
 }
 
+// fp64 throughput probe for the roofline denominators: mode 0 = DFMA chains, mode 1 = DMMA (mma.sync m8n8k4 f64)
+__global__ void __launch_bounds__(256) chd_k_fp64_peak(int mode, int iters, double* sink) {
+  const double s = 1.0 + 1e-9 * threadIdx.x;
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.5 + i;
+  if (mode == 0) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], s, 1e-3);
+    }
+  } else {
+    const double x = s, y = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(a[2 * i]), "+d"(a[2 * i + 1])
+                     : "d"(x), "d"(y));
+    }
+  }
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += a[i];
+  if (t == 123.456) sink[threadIdx.x] = t;
+}
+
 // the elimination window lives in shared memory (WS) or, for very wide bands, in a global scratch buffer
 __global__ void __launch_bounds__(CHD_KKT_THREADS) chd_k_kkt(ChdDev D) { chd_kkt_body<true>(D); }
 __global__ void __launch_bounds__(CHD_KKT_THREADS) chd_k_kkt_gwin(ChdDev D) { chd_kkt_body<false>(D); }

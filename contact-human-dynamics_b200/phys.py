@@ -49,7 +49,17 @@ class _Dims(C.Structure):
 EXPORTS = ["chd_version", "chd_phys_batch_create", "chd_phys_batch_destroy", "chd_phys_get_dims", "chd_phys_get_sizes",
            "chd_phys_get_x", "chd_phys_set_x", "chd_phys_eval", "chd_phys_get_layout", "chd_phys_solve_stage",
            "chd_phys_solve", "chd_phys_sample", "chd_phys_sample_device", "chd_phys_launch_count",
-           "chd_phys_kernel_times", "chd_phys_set_timing", "chd_phys_h2d_bytes", "chd_phys_reset"]
+           "chd_phys_kernel_times", "chd_phys_set_timing", "chd_phys_h2d_bytes", "chd_phys_reset", "chd_measure_fp64_peak"]
+
+
+def measure_fp64_peak():
+    """(DFMA GFLOP/s, DMMA GFLOP/s) sustained on the current device (`chd_measure_fp64_peak`)."""
+    L = load_lib()
+    a, b = C.c_double(0), C.c_double(0)
+    rc = L.chd_measure_fp64_peak(C.byref(a), C.byref(b))
+    if rc != 0:
+        raise RuntimeError("chd_measure_fp64_peak failed with code %d" % rc)
+    return a.value, b.value
 
 
 def lib_path() -> str:

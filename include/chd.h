@@ -142,6 +142,11 @@ int64_t chd_contact_launch_count(const chd_contact_net* net);
 
 const char* chd_version(void);
 
+/* Measurement helper (no reference counterpart): sustained fp64 throughput of the current device in GFLOP/s, for the
+ * scalar FMA pipe (DFMA) and for the fp64 tensor-core instruction the KKT kernel uses (mma.sync m8n8k4, DMMA);
+ * MEASURED_PEAKS.json carries no fp64 figure.  Either output may be NULL. */
+int chd_measure_fp64_peak(double* dfma_gflops, double* dmma_gflops);
+
 #ifdef __cplusplus
 }
 #endif
