@@ -16,6 +16,7 @@ __global__ void chd_k_init(ChdDev D);
 __global__ void chd_k_kkt(ChdDev D);
 __global__ void chd_k_kkt_gwin(ChdDev D);
 __global__ void chd_k_kcopy(ChdDev D);
+__global__ void chd_k_curv(ChdDev D);
 __global__ void chd_k_fp64_peak(int mode, int iters, double* sink);
 __global__ void chd_k_hess_base(ChdDev D);
 __global__ void chd_k_linesearch(ChdDev D);
@@ -39,7 +40,7 @@ struct chd_phys_batch {
   ChdDev D;
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
-  cudaEvent_t ev_kkt = nullptr, ev_copy = nullptr;
+  cudaEvent_t ev_kkt = nullptr, ev_ls = nullptr, ev_copy = nullptr;
   int64_t launches = 0;
   int timing = 0;
   bool host_only = false;
@@ -159,11 +160,16 @@ int run_schedule(chd_phys_batch* b) {
     CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_kkt, 0));
     chd_k_kcopy<<<dim3(b->kcopy_blocks, B), 256, 0, b->copy_stream>>>(b->D);
     b->launches++;
-    CHD_CUDA(cudaEventRecord(b->ev_copy, b->copy_stream));
     {
       Timer t(b, KT_LS);
       chd_k_linesearch<<<B, CHD_THREADS, b->smem_ls, b->stream>>>(b->D);
     }
+    // distance-row curvature of the next iteration needs the accepted iterate: after the line search, on the side stream
+    CHD_CUDA(cudaEventRecord(b->ev_ls, b->stream));
+    CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_ls, 0));
+    chd_k_curv<<<dim3(8, B), 256, 0, b->copy_stream>>>(b->D);
+    b->launches++;
+    CHD_CUDA(cudaEventRecord(b->ev_copy, b->copy_stream));
     {
       Timer t(b, KT_SAMPLE);
       chd_k_snapshot<<<B, 128, 0, b->stream>>>(b->D, b->d_frames);
@@ -248,6 +254,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   CHD_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
   CHD_CUDA(cudaEventCreateWithFlags(&b->ev_kkt, cudaEventDisableTiming));
   CHD_CUDA(cudaEventCreateWithFlags(&b->ev_copy, cudaEventDisableTiming));
+  CHD_CUDA(cudaEventCreateWithFlags(&b->ev_ls, cudaEventDisableTiming));
   CHD_CUDA(cudaEventCreate(&b->ev0));
   CHD_CUDA(cudaEventCreate(&b->ev1));
 #define UP(field) if ((rc = dev_upload(b, hb.field, &D.field))) return rc;
@@ -326,6 +333,7 @@ void chd_phys_batch_destroy(chd_phys_batch* b) {
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->ev_kkt) cudaEventDestroy(b->ev_kkt);
   if (b->ev_copy) cudaEventDestroy(b->ev_copy);
+  if (b->ev_ls) cudaEventDestroy(b->ev_ls);
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;

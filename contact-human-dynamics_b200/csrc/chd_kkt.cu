@@ -81,6 +81,79 @@ __device__ __forceinline__ void chd_stage_advance(const ChdDev& D, ChdIpm& I, in
   else I.phase = CHD_PH_FINISHED;
 }
 
+// y^+ * Jd^T Jd of the squared-distance rows (leg length, toe-heel distance) of sequence b added into K: one warp
+// per active row, rows dealt round-robin to `nw` warps of which this is number `wid`.  ws: 192 doubles of per-warp
+// scratch, slot -> (kkt index, weight, 3-vector column of Jd).  Called from chd_k_kkt (first iteration of a stage)
+// and from chd_k_curv (all later iterations, side stream).
+__device__ __forceinline__ void chd_curv_rows(const ChdDev& D, int b, const ChdKT& K, const ChdStageDev& sg, int wid, int nw, int lane,
+                                              double* ws) {
+  const ChdSeq* h = D.seq + b;
+  const size_t ro = (size_t)b * D.m_max, vo = (size_t)b * D.n_max;
+  const int* vk = D.var_kkt + vo;
+  ChdCtx c;
+  chd_make_ctx(D, b, D.x + vo, c);
+  for (int si = 0; si < h->nsets; ++si) {
+    const ChdSet st = c.sets[si];
+    if (!(sg.set_mask & CHD_MASK(st.type))) continue;
+    if (st.type != CHD_SET_ROM && st.type != CHD_SET_HEEL) continue;
+    const int nslot = st.type == CHD_SET_ROM ? 36 : 24;
+    for (int k = wid; k < st.nitems; k += nw) {
+      const int R = st.row0 + k;
+      const double yc = D.sc[ro + R] * D.y[ro + R];
+      if (!(yc > CHD_CURV_MIN)) continue;
+      const double t = c.t_rom[k];
+      ChdSpl P0, P1, P2;
+      double dRh[3][3];
+      if (st.type == CHD_SET_ROM) {
+        // d = p_ee - R(e) h - c : blocks lin (-B e_dim), ang (-B dR_dim h), ee (+B e_dim)
+        chd_spl_at(c, 0, t, P0);
+        chd_spl_at(c, 1, t, P1);
+        chd_spl_at(c, chd_sp_motion(st.a), t, P2);
+        double e[3];
+        chd_spl_val(c, P1, 0, e);
+        ChdTrig tr;
+        chd_trig(e, tr);
+        const double* hip = chd_hip(c, st.a, t);
+        for (int j = 0; j < 3; ++j) {
+          double Dj[9];
+          chd_dR(tr, j, Dj);
+          chd_mv(Dj, hip, dRh[j]);
+        }
+      } else {
+        chd_spl_at(c, chd_sp_motion(st.a), t, P0);   // d = p_a - p_b
+        chd_spl_at(c, chd_sp_motion(st.b), t, P1);
+      }
+      for (int a = lane; a < nslot; a += 32) {
+        const int ba = a / 12, qa = a % 12, da = qa % 3;
+        const ChdSpl& Pa = ba == 0 ? P0 : (ba == 1 ? P1 : P2);
+        const int va = Pa.var[qa];
+        const int ia = va >= 0 ? vk[va] : -1;
+        double sgn, v3[3] = {da == 0 ? 1.0 : 0.0, da == 1 ? 1.0 : 0.0, da == 2 ? 1.0 : 0.0};
+        if (st.type == CHD_SET_ROM) {
+          sgn = ba == 2 ? 1.0 : -1.0;
+          if (ba == 1) v3[0] = dRh[da][0], v3[1] = dRh[da][1], v3[2] = dRh[da][2];
+        } else {
+          sgn = ba == 0 ? 1.0 : -1.0;
+        }
+        ws[a * 5 + 0] = (double)ia;
+        ws[a * 5 + 1] = ia >= 0 ? sgn * chd_slot_w(Pa, 0, qa) : 0.0;
+        ws[a * 5 + 2] = v3[0], ws[a * 5 + 3] = v3[1], ws[a * 5 + 4] = v3[2];
+      }
+      __syncwarp();
+      for (int idx = lane; idx < nslot * nslot; idx += 32) {
+        const int a = idx / nslot, bq = idx - a * nslot;
+        const double wa = ws[a * 5 + 1], wb = ws[bq * 5 + 1];
+        if (wa == 0.0 || wb == 0.0) continue;
+        const int ia = (int)ws[a * 5], ib = (int)ws[bq * 5];
+        if (ia < ib) continue;
+        const double dotv = ws[a * 5 + 2] * ws[bq * 5 + 2] + ws[a * 5 + 3] * ws[bq * 5 + 3] + ws[a * 5 + 4] * ws[bq * 5 + 4];
+        if (dotv != 0.0) chd_kadd(K, ia, ib, yc * wa * wb * dotv);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // dynamic shared memory layout of chd_k_kkt (doubles):
 //   red[CHD_KKT_THREADS] | vecn[n_max] | xs[Np_max + nbp8] | cc[nbp8*nbp8] | ypan[(Q+nbt)*64] | xpan[(Q+nbt)*64] | xs2[Np_max] | dinv[16]
 //   | win[Q(Q+1)/2 * 64] | bwin[Q*nbt*64]            (the last two in global scratch when they do not fit)
@@ -91,6 +164,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   const int b = blockIdx.x;
   ChdIpm& I = D.ipm[b];
   if (I.phase != CHD_PH_RUN) return;
+  const int pre_refreshed = I.kw_req;   // Kwork = Kbase + distance-row curvature already prepared on the side stream
   const ChdStageDev sg = D.stages[I.stage];
   const ChdSeq* h = D.seq + b;
   const int n = h->n, m = h->m, tid = threadIdx.x, nt = blockDim.x;
@@ -209,7 +283,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   // (J^T Sigma J); wide ones (leg length) keep their multiplier as an unknown with diagonal
   // -1/Sigma, which needs 36 instead of 666 matrix updates per row.  The right-hand side is accumulated in
   // shared memory (xs) and written out once.
-  if (!I.kw_req) {   // first iteration of a stage; afterwards chd_k_kcopy refreshes Kwork on the side stream
+  if (!pre_refreshed) {   // first iteration of a stage; afterwards chd_k_kcopy refreshes Kwork on the side stream
     const double* base = D.Kbase + (size_t)b * D.kstride;
     const double2* src = reinterpret_cast<const double2*>(base);
     double2* dst = reinterpret_cast<double2*>(kw);
@@ -297,73 +371,9 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   for (int i = tid; i < K.Np; i += nt) K.bord[((size_t)(i >> 3) * nbt + (NBR >> 3)) * 64 + (NBR & 7) * 8 + (i & 7)] = i < Na ? rhs_s[i] : 0.0;
   for (int i = tid; i < nbl; i += nt) K.corn[(size_t)NBR * nbp8 + i] = rhs_s[8 * D.nbc_max + i];
   CHD_PROF(1);
-  // y^+ * Jd^T Jd of the squared-distance rows (leg length, toe-heel distance): one warp per active row.
-  // per-warp scratch (in the not yet used window memory): slot -> (kkt index, weight, 3-vector column of Jd)
-  {
-    ChdCtx c;
-    chd_make_ctx(D, b, D.x + vo, c);
-    double* ws = win + warp * 192;
-    for (int si = 0; si < h->nsets; ++si) {
-      const ChdSet st = c.sets[si];
-      if (!(sg.set_mask & CHD_MASK(st.type))) continue;
-      if (st.type != CHD_SET_ROM && st.type != CHD_SET_HEEL) continue;
-      const int nslot = st.type == CHD_SET_ROM ? 36 : 24;
-      for (int k = warp; k < st.nitems; k += nwarp) {
-        const int R = st.row0 + k;
-        const double yc = D.sc[ro + R] * D.y[ro + R];
-        if (!(yc > CHD_CURV_MIN)) continue;
-        const double t = c.t_rom[k];
-        ChdSpl P0, P1, P2;
-        double dRh[3][3];
-        if (st.type == CHD_SET_ROM) {
-          // d = p_ee - R(e) h - c : blocks lin (-B e_dim), ang (-B dR_dim h), ee (+B e_dim)
-          chd_spl_at(c, 0, t, P0);
-          chd_spl_at(c, 1, t, P1);
-          chd_spl_at(c, chd_sp_motion(st.a), t, P2);
-          double e[3];
-          chd_spl_val(c, P1, 0, e);
-          ChdTrig tr;
-          chd_trig(e, tr);
-          const double* hip = chd_hip(c, st.a, t);
-          for (int j = 0; j < 3; ++j) {
-            double Dj[9];
-            chd_dR(tr, j, Dj);
-            chd_mv(Dj, hip, dRh[j]);
-          }
-        } else {
-          chd_spl_at(c, chd_sp_motion(st.a), t, P0);   // d = p_a - p_b
-          chd_spl_at(c, chd_sp_motion(st.b), t, P1);
-        }
-        for (int a = lane; a < nslot; a += 32) {
-          const int ba = a / 12, qa = a % 12, da = qa % 3;
-          const ChdSpl& Pa = ba == 0 ? P0 : (ba == 1 ? P1 : P2);
-          const int va = Pa.var[qa];
-          const int ia = va >= 0 ? vk[va] : -1;
-          double sgn, v3[3] = {da == 0 ? 1.0 : 0.0, da == 1 ? 1.0 : 0.0, da == 2 ? 1.0 : 0.0};
-          if (st.type == CHD_SET_ROM) {
-            sgn = ba == 2 ? 1.0 : -1.0;
-            if (ba == 1) v3[0] = dRh[da][0], v3[1] = dRh[da][1], v3[2] = dRh[da][2];
-          } else {
-            sgn = ba == 0 ? 1.0 : -1.0;
-          }
-          ws[a * 5 + 0] = (double)ia;
-          ws[a * 5 + 1] = ia >= 0 ? sgn * chd_slot_w(Pa, 0, qa) : 0.0;
-          ws[a * 5 + 2] = v3[0], ws[a * 5 + 3] = v3[1], ws[a * 5 + 4] = v3[2];
-        }
-        __syncwarp();
-        for (int idx = lane; idx < nslot * nslot; idx += 32) {
-          const int a = idx / nslot, bq = idx - a * nslot;
-          const double wa = ws[a * 5 + 1], wb = ws[bq * 5 + 1];
-          if (wa == 0.0 || wb == 0.0) continue;
-          const int ia = (int)ws[a * 5], ib = (int)ws[bq * 5];
-          if (ia < ib) continue;
-          const double dotv = ws[a * 5 + 2] * ws[bq * 5 + 2] + ws[a * 5 + 3] * ws[bq * 5 + 3] + ws[a * 5 + 4] * ws[bq * 5 + 4];
-          if (dotv != 0.0) chd_kadd(K, ia, ib, yc * wa * wb * dotv);
-        }
-        __syncwarp();
-      }
-    }
-  }
+  // y^+ * Jd^T Jd of the squared-distance rows: in-kernel only on the first iteration of a stage, afterwards
+  // chd_k_curv has already added them on the side stream (many CTAs per sequence: the atomics are the cost)
+  if (!pre_refreshed) chd_curv_rows(D, b, K, sg, warp, nwarp, lane, win + warp * 192);
   __threadfence_block();
   __syncthreads();
   CHD_PROF(2);
@@ -732,6 +742,19 @@ __global__ void __launch_bounds__(256) chd_k_kcopy(ChdDev D) {
     dst[i] = v0, dst[i + nt] = v1, dst[i + 2 * nt] = v2, dst[i + 3 * nt] = v3;
   }
   for (; i < hi; i += nt) dst[i] = src[i];
+}
+
+// distance-row curvature terms of the next iteration (needs the iterate the line search just accepted); side stream,
+// after chd_k_kcopy, grid (G, B)
+__global__ void __launch_bounds__(256) chd_k_curv(ChdDev D) {
+  __shared__ double s_ws[8 * 192];
+  const int b = blockIdx.y;
+  const ChdIpm& I = D.ipm[b];
+  if (!I.kw_req || I.phase != CHD_PH_RUN) return;
+  ChdKT K;
+  chd_kt_init(D, D.seq + b, D.Kwork + (size_t)b * D.kstride, K);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  chd_curv_rows(D, b, K, D.stages[I.stage], blockIdx.x * 8 + warp, gridDim.x * 8, lane, s_ws + warp * 192);
 }
 
 // fp64 throughput probe for the roofline denominators: mode 0 = DFMA chains, mode 1 = DMMA (mma.sync m8n8k4 f64)
