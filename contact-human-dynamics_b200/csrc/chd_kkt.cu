@@ -418,6 +418,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     double* Bk = bwin + (size_t)kslot * nbt * 64;
     const double* dv = dinv + 8 * cur;
     // (b) panel rows: x = a L0^-T D^-1 -> xpan + global (final L), y = a L0^-T -> ypan; diag tile -> global
+    long long tp0 = clock64();
     for (int row = tid; row < 8 * tq + nbp8; row += nt) {
       const bool band_row = row < 8 * tq;
       const int prow = band_row ? row : 8 * GB + row - 8 * tq;       // row id inside the panel buffers
@@ -429,11 +430,14 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       double* gdst = band_row ? K.band + ((size_t)Kc * Q + 1) * 64 + row * 8 : K.bord + (size_t)Kc * nbt * 64 + (row - 8 * tq) * 8;
       bool nzr = false;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) xpan[prow * 8 + c] = a8[c], gdst[c] = a8[c], nzr = nzr || a8[c] != 0.0;
+      for (int c = 0; c < 8; ++c) gdst[c] = a8[c], nzr = nzr || a8[c] != 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(xpan + prow * 8)[j] = make_double2(a8[j], a8[j + 4]);   // fragment order
       if (nzr) s_gnz[cur][prow >> 3] = 1;
     }
     for (int e = tid; e < 64; e += nt) K.band[(size_t)Kc * Q * 64 + e] = Tkk[e];
     __syncthreads();
+    long long tp1 = clock64();
     // (c) stream in block row Kc + Q (its slots are dead now), trailing updates on the fp64 tensor core;
     //     warp 0 takes the pair that completes the next diagonal tile and factors it right away
     const int In = Kc + Q;
@@ -531,25 +535,33 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
               Cp[i][r8] = c0[i], Cp[i][r8 + 1] = c1[i];
             }
         }
-      } else
-      for (int p = warp - 1; p < np_loop; p += nwarp - 1) {
-        const int ai = s_pairs[p] >> 8, aj = s_pairs[p] & 255;
-        int gi, gj;
-        if (compact) {
-          gi = __shfl_sync(0xffffffffu, myg, ai), gj = __shfl_sync(0xffffffffu, myg, aj);
-        } else {
-          gi = ai, gj = aj;
-          if ((gi < GB && gi >= tq) || (gj < GB && gj >= tq) || !gnz[gi] || !gnz[gj]) continue;
-        }
-        if (gi == 0 && gj == 0) continue;   // the next diagonal tile is updated by warp 0
-        const double* X = xpan + gi * 64;
-        const double* Y = ypan + gj * 64;
-        if (gi < GB) {
-          chd_tile_sub_xyT(win + (size_t)tri(rs[gi], rs[gj]) * 64, X, Y, lane);
-        } else if (gj < GB) {
-          chd_tile_sub_xyT(bwin + ((size_t)rs[gj] * nbt + (gi - GB)) * 64, X, Y, lane);
-        } else {
-          const int bi = gi - GB, bj = gj - GB;  // corner block: strided rows, scalar code
+      } else {
+        // window in shared memory: two target tiles per loop trip with interleaved tensor-core updates (the dependent
+        // chain index -> tile address -> load -> 2 x DMMA -> store of a single tile leaves the pipe idle most of the time)
+        auto decode = [&](int p, double*& C, const double*& X, const double*& Y, int& bi, int& bj) -> int {
+          const int ai = s_pairs[p] >> 8, aj = s_pairs[p] & 255;
+          int gi, gj;
+          if (compact) {
+            gi = __shfl_sync(0xffffffffu, myg, ai), gj = __shfl_sync(0xffffffffu, myg, aj);
+          } else {
+            gi = ai, gj = aj;
+            if ((gi < GB && gi >= tq) || (gj < GB && gj >= tq) || !gnz[gi] || !gnz[gj]) return 0;
+          }
+          if (gi == 0 && gj == 0) return 0;   // the next diagonal tile is updated by warp 0
+          X = xpan + gi * 64;
+          Y = ypan + gj * 64;
+          if (gi < GB) {
+            C = win + (size_t)tri(rs[gi], rs[gj]) * 64;
+            return 1;
+          }
+          if (gj < GB) {
+            C = bwin + ((size_t)rs[gj] * nbt + (gi - GB)) * 64;
+            return 1;
+          }
+          bi = gi - GB, bj = gj - GB;
+          return 2;
+        };
+        auto corner = [&](const double* X, const double* Y, int bi, int bj) {   // corner block: strided rows, scalar code
           for (int e = lane; e < 64; e += 32) {
             const int r = e >> 3, cq = e & 7;
             double acc = 0.0;
@@ -557,11 +569,40 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
             for (int kk = 0; kk < 8; ++kk) acc += X[r * 8 + kk] * Y[cq * 8 + kk];
             cc[(bi * 8 + r) * nbp8 + bj * 8 + cq] -= acc;
           }
+        };
+        const int step = nwarp - 1, r8 = (lane >> 2) * 8 + 2 * (lane & 3);
+        for (int p = warp - 1; p < np_loop; p += 2 * step) {
+          double *C1 = nullptr, *C2 = nullptr;
+          const double *X1 = nullptr, *Y1 = nullptr, *X2 = nullptr, *Y2 = nullptr;
+          int b1i = 0, b1j = 0, b2i = 0, b2j = 0;
+          const int k1 = decode(p, C1, X1, Y1, b1i, b1j);
+          const int k2 = p + step < np_loop ? decode(p + step, C2, X2, Y2, b2i, b2j) : 0;
+          if (k1 == 1 && k2 == 1) {
+            double2 c1 = *reinterpret_cast<const double2*>(C1 + r8), c2 = *reinterpret_cast<const double2*>(C2 + r8);
+            const double2 xa1 = *reinterpret_cast<const double2*>(X1 + 2 * lane), yb1 = *reinterpret_cast<const double2*>(Y1 + 2 * lane);
+            const double2 xa2 = *reinterpret_cast<const double2*>(X2 + 2 * lane), yb2 = *reinterpret_cast<const double2*>(Y2 + 2 * lane);
+            asm volatile(
+                "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%4}, {%5}, {%0,%1};\n\t"
+                "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%6}, {%7}, {%2,%3};\n\t"
+                "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%8}, {%9}, {%0,%1};\n\t"
+                "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%10}, {%11}, {%2,%3};"
+                : "+d"(c1.x), "+d"(c1.y), "+d"(c2.x), "+d"(c2.y)
+                : "d"(-xa1.x), "d"(yb1.x), "d"(-xa2.x), "d"(yb2.x), "d"(-xa1.y), "d"(yb1.y), "d"(-xa2.y), "d"(yb2.y));
+            *reinterpret_cast<double2*>(C1 + r8) = c1;
+            *reinterpret_cast<double2*>(C2 + r8) = c2;
+          } else {
+            if (k1 == 1) chd_tile_sub_xyT(C1, X1, Y1, lane);
+            if (k2 == 1) chd_tile_sub_xyT(C2, X2, Y2, lane);
+          }
+          if (k1 == 2) corner(X1, Y1, b1i, b1j);
+          if (k2 == 2) corner(X2, Y2, b2i, b2j);
         }
       }
     }
+    long long tp2 = clock64();
     chd_copy_wait(WS);
     __syncthreads();
+    if (tid == 32) { long long tp3 = clock64(); I.prof[8] += (double)(tp1 - tp0), I.prof[9] += (double)(tp2 - tp1), I.prof[10] += (double)(tp3 - tp2); }
     kslot = kslot + 1 == Q ? 0 : kslot + 1;
   }
   CHD_PROF(3);

@@ -54,17 +54,21 @@ __device__ __forceinline__ void chd_radd(const ChdKT& K, int i, double v) {  // 
 // D(8x8) = C - X * Y^T for row-major 8x8 tiles X, Y (fp64 tensor core, two k-steps of m8n8k4).
 // Fragment layout (PTX ISA, mma.m8n8k4 f64): A[row = lane>>2][k = lane&3], B[k = lane&3][col = lane>>2],
 // C/D[row = lane>>2][col = 2*(lane&3) + {0,1}].
-// accumulator form: (c0, c1) -= (X Y^T)[r][2k, 2k+1]
+// accumulator form: (c0, c1) -= (X Y^T)[r][2k, 2k+1].
+// X and Y are panel tiles in *fragment order*: element (row r, column c) of the 8x8 tile sits at
+// r*8 + chd_frag_col(c), so that lane (r = lane>>2, k = lane&3) finds its two operands {c = k, c = k+4} of both
+// k-steps in one aligned 16-byte word at [2*lane] -- a conflict-free LDS.128 instead of two 4-way bank-conflicted
+// 8-byte loads per operand (the trailing updates were shared-memory bound on exactly those conflicts).
+__device__ __forceinline__ int chd_frag_col(int c) { return ((c & 3) << 1) | (c >> 2); }
 __device__ __forceinline__ void chd_tile_mma(double& c0, double& c1, const double* X, const double* Y, int lane) {
-  const int r = lane >> 2, k = lane & 3;
-#pragma unroll
-  for (int kk = 0; kk < 8; kk += 4) {
-    const double a = -X[r * 8 + kk + k];
-    const double b = Y[r * 8 + kk + k];
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-  }
+  const double2 xa = *reinterpret_cast<const double2*>(X + 2 * lane);
+  const double2 yb = *reinterpret_cast<const double2*>(Y + 2 * lane);
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(-xa.x), "d"(yb.x));
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(-xa.y), "d"(yb.y));
 }
 __device__ __forceinline__ void chd_tile_sub_xyT(double* C, const double* X, const double* Y, int lane) {
   const int r = lane >> 2, k = lane & 3;
@@ -104,7 +108,8 @@ __device__ __forceinline__ bool chd_tile_ldl(double* T, double* dinv, int lane) 
   return ok;
 }
 
-// One panel row: y = a L0^-T (unit lower L0 in tile T0), x = y * dinv.  Writes x in place, y to yout.
+// One panel row: y = a L0^-T (unit lower L0 in tile T0), x = y * dinv.  Writes x in place, y to yout (fragment order,
+// see chd_tile_mma).
 // Right-looking form: once y[p] is final it is eliminated from all later entries at once, so the dependent
 // chain is 7 fused multiply-adds long instead of 28.
 __device__ __forceinline__ void chd_row_trsm(double* a_row, const double* T0, const double* dinv, double* yout) {
@@ -117,10 +122,9 @@ __device__ __forceinline__ void chd_row_trsm(double* a_row, const double* T0, co
     for (int c = p + 1; c < 8; ++c) y[c] -= y[p] * T0[c * 8 + p];
   }
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    yout[c] = y[c];
-    a_row[c] = y[c] * dinv[c];
-  }
+  for (int c = 0; c < 8; ++c) a_row[c] = y[c] * dinv[c];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(yout)[j] = make_double2(y[j], y[j + 4]);   // fragment order
 }
 
 // 16-byte copy global -> window.  With the window in shared memory this is an asynchronous cp.async (LDGSTS);
