@@ -29,8 +29,7 @@ struct ChdIpm {
   double f, E0, viol_u, dual_u, compl_u;          // error measures at the current iterate
   double phi0, theta0, dphi, a_pr, a_du;          // line-search inputs produced by the KKT kernel
   double filt[2 * CHD_FILT_MAX];
-  double prof[12];  // clock64 cycles per phase of chd_k_kkt (0 errors, 1 J assembly, 2 Hessian assembly, 3 factor, 4 border, 5 back-subst,
-                    // 6 step recovery, 7 warp 0 diagonal tile, 8 panel phase, 9 trailing updates of warp 1, 10 its wait at the barrier)
+  double prof[8];   // clock64 cycles per phase of chd_k_kkt (0 errors, 1 J assembly, 2 Hessian assembly, 3 factor, 4 border, 5 back-subst, 6 step recovery)
 };
 
 struct ChdStageDev {

@@ -48,7 +48,7 @@ __global__ void chd_k_stage_begin(ChdDev D) {
     I.delta_w = CHD_DELTA_W0;
     I.mu_filter = -1.0;
     I.sf = 1.0;
-    for (int q = 0; q < 12; ++q) I.prof[q] = 0.0;
+    for (int q = 0; q < 8; ++q) I.prof[q] = 0.0;
     for (int q = 40; q < 48; ++q) I.filt[q] = 0.0;
   }
 }
