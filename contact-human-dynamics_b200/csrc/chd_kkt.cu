@@ -396,6 +396,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   __shared__ int s_gnz[2][96];   // per panel group: any non-zero entry in the X tile (zero tiles skip their trailing updates)
   __shared__ unsigned short s_pairs[3000];
   __shared__ unsigned char s_cmp[CHD_KKT_THREADS / 32][32];
+  __shared__ __align__(16) double s_winv[2][64];   // inverse of the current / next diagonal tile factor, fragment order
   const int GB = K.q, Gm = K.q + nbt, npairs = Gm * (Gm + 1) / 2;
   for (int p = tid; p < npairs && p < 3000; p += nt) {
     int gi = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
@@ -407,7 +408,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   for (int g = tid; g < GB; g += nt) s_rs[0][g] = (1 + g) % Q;
   for (int g = tid; g < 96; g += nt) s_gnz[0][g] = 0, s_gnz[1][g] = 0;
   if (warp == 0) {
-    const bool ok = chd_tile_ldl(win, dinv, lane);   // tile (0,0) sits in slot 0
+    const bool ok = chd_tile_ldl(win, dinv, s_winv[0], lane);   // tile (0,0) sits in slot 0
     if (!ok && lane == 0) s_fail = 1;
   }
   __syncthreads();
@@ -418,22 +419,35 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     double* Tkk = win + (size_t)tri(kslot, kslot) * 64;
     double* Bk = bwin + (size_t)kslot * nbt * 64;
     const double* dv = dinv + 8 * cur;
-    // (b) panel rows: x = a L0^-T D^-1 -> xpan + global (final L), y = a L0^-T -> ypan; diag tile -> global
-    for (int row = tid; row < 8 * tq + nbp8; row += nt) {
-      const bool band_row = row < 8 * tq;
-      const int prow = band_row ? row : 8 * GB + row - 8 * tq;       // row id inside the panel buffers
-      const double* src = band_row ? win + (size_t)tri(rs[row >> 3], kslot) * 64 + (row & 7) * 8 : Bk + (row - 8 * tq) * 8;
-      double a8[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) a8[c] = src[c];
-      chd_row_trsm(a8, Tkk, dv, ypan + prow * 8);
-      double* gdst = band_row ? K.band + ((size_t)Kc * Q + 1) * 64 + row * 8 : K.bord + (size_t)Kc * nbt * 64 + (row - 8 * tq) * 8;
-      bool nzr = false;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) gdst[c] = a8[c], nzr = nzr || a8[c] != 0.0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(xpan + prow * 8)[j] = make_double2(a8[j], a8[j + 4]);   // fragment order
-      if (nzr) s_gnz[cur][prow >> 3] = 1;
+    // (b) panel: Y = A L0^-T = A W^T (W = L0^-1 from the diagonal-tile factorisation) as one tensor-core product per
+    //     8x8 panel tile, X = Y D^-1; both go to the panel buffers in fragment order, X also to global (final L);
+    //     the diagonal tile goes to global as well
+    {
+      const double* wv = s_winv[cur];
+      const int r = lane >> 2, k = lane & 3;
+      const double2 wf = *reinterpret_cast<const double2*>(wv + 2 * lane);
+      const double d0 = dv[2 * k], d1 = dv[2 * k + 1];
+      const int f0 = r * 8 + chd_frag_col(2 * k), f1 = r * 8 + chd_frag_col(2 * k + 1);
+      for (int g = warp; g < tq + nbt; g += nwarp) {
+        const bool band_t = g < tq;
+        const int pg = band_t ? g : GB + (g - tq);                   // group id inside the panel buffers
+        const double* A = band_t ? win + (size_t)tri(rs[g], kslot) * 64 : Bk + (g - tq) * 64;
+        const double ax = A[r * 8 + k], ay = A[r * 8 + k + 4];
+        double c0 = 0.0, c1 = 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1)
+                     : "d"(ax), "d"(wf.x));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1)
+                     : "d"(ay), "d"(wf.y));
+        const double x0 = c0 * d0, x1 = c1 * d1;
+        ypan[pg * 64 + f0] = c0, ypan[pg * 64 + f1] = c1;
+        xpan[pg * 64 + f0] = x0, xpan[pg * 64 + f1] = x1;
+        double* G = band_t ? K.band + ((size_t)Kc * Q + 1 + g) * 64 : K.bord + ((size_t)Kc * nbt + (g - tq)) * 64;
+        *reinterpret_cast<double2*>(G + r * 8 + 2 * k) = make_double2(x0, x1);
+        const bool nz = __any_sync(0xffffffffu, x0 != 0.0 || x1 != 0.0);
+        if (lane == 0 && nz) s_gnz[cur][pg] = 1;
+      }
     }
     for (int e = tid; e < 64; e += nt) K.band[(size_t)Kc * Q * 64 + e] = Tkk[e];
     __syncthreads();
@@ -458,7 +472,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
         double* Tn = win + (size_t)tri(rs[0], rs[0]) * 64;
         chd_tile_sub_xyT(Tn, xpan, ypan, lane);
         __syncwarp();
-        const bool ok = chd_tile_ldl(Tn, dinv + 8 * (cur ^ 1), lane);
+        const bool ok = chd_tile_ldl(Tn, dinv + 8 * (cur ^ 1), s_winv[cur ^ 1], lane);
         if (!ok && lane == 0) s_fail = 1;
       }
     } else {

@@ -79,8 +79,10 @@ __device__ __forceinline__ void chd_tile_sub_xyT(double* C, const double* X, con
 }
 
 // In-place LDL^T of the lower triangle of an 8x8 row-major tile by one warp (lanes replicate rows r = lane&7).
-// On exit: strict lower part = unit L, diagonal = d.  dinv[8] receives 1/d.  Returns false on a bad pivot.
-__device__ __forceinline__ bool chd_tile_ldl(double* T, double* dinv, int lane) {
+// On exit: strict lower part = unit L, diagonal = d.  dinv[8] receives 1/d and winv[64] the inverse W = L^-1
+// (unit lower triangular) in fragment order, so that the panel below the tile becomes one tensor-core product
+// Y = A W^T per 8x8 panel tile instead of a scalar triangular solve per row.  Returns false on a bad pivot.
+__device__ __forceinline__ bool chd_tile_ldl(double* T, double* dinv, double* winv, int lane) {
   const int r = lane & 7;
   double a[8];
 #pragma unroll
@@ -105,26 +107,23 @@ __device__ __forceinline__ bool chd_tile_ldl(double* T, double* dinv, int lane) 
     for (int c = 0; c < 8; ++c)
       if (c <= r) T[r * 8 + c] = a[c];
   }
-  return ok;
-}
-
-// One panel row: y = a L0^-T (unit lower L0 in tile T0), x = y * dinv.  Writes x in place, y to yout (fragment order,
-// see chd_tile_mma).
-// Right-looking form: once y[p] is final it is eliminated from all later entries at once, so the dependent
-// chain is 7 fused multiply-adds long instead of 28.
-__device__ __forceinline__ void chd_row_trsm(double* a_row, const double* T0, const double* dinv, double* yout) {
-  double y[8];
+  // W = L^-1 by forward substitution on the rows: w = e_r - sum_{j<r} L[r][j] W[j][:], row j is final at step j
+  double w[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) y[c] = a_row[c];
+  for (int c = 0; c < 8; ++c) w[c] = c == r ? 1.0 : 0.0;
 #pragma unroll
-  for (int p = 0; p < 7; ++p) {
+  for (int j = 0; j < 7; ++j) {
 #pragma unroll
-    for (int c = p + 1; c < 8; ++c) y[c] -= y[p] * T0[c * 8 + p];
+    for (int c = 0; c <= j; ++c) {
+      const double wjc = __shfl_sync(0xffffffffu, w[c], j, 8);
+      if (r > j) w[c] -= a[j] * wjc;
+    }
   }
+  if (lane < 8) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) a_row[c] = y[c] * dinv[c];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(yout)[j] = make_double2(y[j], y[j + 4]);   // fragment order
+    for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(winv + r * 8)[j] = make_double2(w[j], w[j + 4]);   // fragment order
+  }
+  return ok;
 }
 
 // 16-byte copy global -> window.  With the window in shared memory this is an asynchronous cp.async (LDGSTS);
