@@ -706,52 +706,62 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       for (int q2 = 0; q2 < nbl; ++q2) v -= bt[q2 * 8] * xb[q2];
       accv[i] = v;
     }
-    // staging buffers in the (now free) window: stg[buf] = diag tile | tiles (K, K-1-g), g = 0..q-1
+    // staging buffers in the (now free) window + border window: two chunks of R block rows each,
+    // row slot = diag tile | tiles (K, K-1-g), g = 0..q-1.  Warp 0 alone walks through a chunk (the recursion is
+    // sequential anyway; without block barriers a block row costs ~0.5 k cycles instead of 1.4 k) while the other
+    // warps prefetch the next chunk; one barrier per chunk.
     const int per = Q * 64;
+    const int R = max(1, (D.win_tiles + Q * nbt) / (2 * Q));
     double* stg = win;
-    auto stage_row = [&](int Kr, int buf) {
-      if (Kr < 0) return;
-      for (int idx = tid; idx < Q * 32; idx += nt) {
-        const int tile = idx >> 5, off = (idx & 31) * 2;
+    auto stage_chunk = [&](int Ktop, int buf, int t0, int tstep) {   // block rows Ktop, Ktop-1, ... (R of them)
+      for (int idx = t0; idx < R * Q * 32; idx += tstep) {
+        const int rr = idx / (Q * 32), rem = idx - rr * (Q * 32);
+        const int Kr = Ktop - rr;
+        if (Kr < 0) break;
+        const int tile = rem >> 5, off = (rem & 31) * 2;
         const int J = tile == 0 ? Kr : Kr - tile;     // tile 0: diagonal; tile g+1: (Kr, Kr-1-g)
         if (J < 0) continue;
-        chd_copy16(stg + (size_t)buf * per + tile * 64 + off, K.band + ((size_t)J * Q + (Kr - J)) * 64 + off, WS);
+        chd_copy16(stg + ((size_t)buf * R + rr) * per + tile * 64 + off, K.band + ((size_t)J * Q + (Kr - J)) * 64 + off, WS);
       }
     };
-    stage_row(nbc - 1, 0);
+    stage_chunk(nbc - 1, 0, tid, nt);
     chd_copy_wait(WS);
     __syncthreads();
     int buf = 0;
-    for (int Kc = nbc - 1; Kc >= 0; --Kc, buf ^= 1) {
-      const double* T0 = stg + (size_t)buf * per;
-      stage_row(Kc - 1, buf ^ 1);
-      if (warp == 0) {
-        double xk[8];
+    for (int Ktop = nbc - 1; Ktop >= 0; Ktop -= R, buf ^= 1) {
+      if (warp != 0) {
+        stage_chunk(Ktop - R, buf ^ 1, tid - 32, nt - 32);
+      } else {
+        for (int rr = 0; rr < R && Ktop - rr >= 0; ++rr) {
+          const int Kc = Ktop - rr;
+          const double* T0 = stg + ((size_t)buf * R + rr) * per;
+          double xk[8];
 #pragma unroll
-        for (int c = 7; c >= 0; --c) {
-          double v = accv[Kc * 8 + c];
+          for (int c = 7; c >= 0; --c) {
+            double v = accv[Kc * 8 + c];
 #pragma unroll
-          for (int p = c + 1; p < 8; ++p) v -= T0[p * 8 + c] * xk[p];
-          xk[c] = v;
+            for (int p = 7; p > c; --p) v -= T0[p * 8 + c] * xk[p];   // oldest unknown first: only the last link waits for xk[c+1]
+            xk[c] = v;
+          }
+          if (lane < 8) {
+            const int gi = Kc * 8 + lane;
+            double v = xk[0];
+#pragma unroll
+            for (int c = 1; c < 8; ++c) v = lane == c ? xk[c] : v;
+            xs[gi] = v;
+            if (gi < Na) sol[gi] = v;
+          }
+          const int nrow = min(K.q, Kc);   // tiles (Kc, Kc-1-g), g < nrow
+          for (int idx = lane; idx < nrow * 8; idx += 32) {
+            const int g = idx >> 3, c = idx & 7;
+            const double* T = T0 + (g + 1) * 64;
+            double v = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v += T[r * 8 + c] * xk[r];
+            accv[(Kc - 1 - g) * 8 + c] -= v;
+          }
+          __syncwarp();
         }
-        if (lane < 8) {
-          const int gi = Kc * 8 + lane;
-          double v = xk[0];
-#pragma unroll
-          for (int c = 1; c < 8; ++c) v = lane == c ? xk[c] : v;
-          xs[gi] = v;
-          if (gi < Na) sol[gi] = v;
-        }
-      }
-      __syncthreads();
-      const int nrow = min(K.q, Kc);   // tiles (Kc, Kc-1-g), g < nrow
-      for (int idx = tid; idx < nrow * 8; idx += nt) {
-        const int g = idx >> 3, c = idx & 7;
-        const double* T = T0 + (g + 1) * 64;
-        double v = 0.0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v += T[r * 8 + c] * xs[Kc * 8 + r];
-        accv[(Kc - 1 - g) * 8 + c] -= v;
       }
       chd_copy_wait(WS);
       __syncthreads();
