@@ -259,7 +259,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   CHD_CUDA(cudaEventCreate(&b->ev1));
 #define UP(field) if ((rc = dev_upload(b, hb.field, &D.field))) return rc;
   UP(seq) UP(poly_T) UP(poly_tend) UP(node_const) UP(par) UP(t_dyn) UP(t_rom) UP(t_data) UP(row_lo) UP(row_hi) UP(node_var)
-  UP(itab) UP(ent_ptr) UP(ent_col) UP(var_kkt) UP(row_kkt) UP(row_set) UP(sets) UP(phase_tend)
+  UP(itab) UP(ent_ptr) UP(ent_col) UP(ent_row) UP(col_ptr) UP(col_ent) UP(var_kkt) UP(row_kkt) UP(row_set) UP(sets) UP(phase_tend)
 #undef UP
   const size_t B = hb.B, nm = B * hb.n_max, mm = B * hb.m_max;
 #define AL(field, cnt) if ((rc = dev_alloc(b, (cnt), &D.field))) return rc;

@@ -48,6 +48,7 @@ struct ChdDev {
   const ChdSeq* seq;
   const double *poly_T, *poly_tend, *node_const, *par, *t_dyn, *t_rom, *t_data, *row_lo, *row_hi;
   const int *node_var, *itab, *ent_ptr, *ent_col, *var_kkt, *row_kkt, *row_set;
+  const int *ent_row, *col_ptr, *col_ent;      // row of every slot; slots by column
   const ChdSet* sets;
   const double* phase_tend;                   // B x n_ee_max x Ph_max cumulative phase end times
   // ---- iterate ----

@@ -202,21 +202,23 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
 #define CHD_PROF(slot) do { __syncthreads(); if (tid == 0) { long long t_ = clock64(); I.prof[slot] += (double)(t_ - tk0); tk0 = t_; } } while (0)
 
   // ---------------- A. error measures, convergence, barrier update ----------------
-  for (int i = tid; i < n; i += nt) vecn[i] = sf * grad[i];
-  __syncthreads();
+  // J^T y is gathered per variable from a column-oriented index of the Jacobian slots (no shared-memory fp64
+  // atomics, which are compare-and-swap loops): per-row multipliers first, into the (idle) dy array
+  const int* erow = D.ent_row + (size_t)b * D.slots_max;
+  const int* cptr = D.col_ptr + (size_t)b * (D.n_max + 1);
+  const int* cent = D.col_ent + (size_t)b * D.slots_max;
+  double* rowv = D.dy + ro;
   double a_ysum = 0, a_zsum = 0, a_cviol = 0, a_theta = 0, a_rs = 0, a_cmax = -INFINITY, a_cmin = INFINITY, a_violu = 0;
   for (int r = tid; r < m; r += nt) {
     const int f = rf[r];
-    if (!(f & CHD_ROW_ACTIVE)) continue;
+    if (!(f & CHD_ROW_ACTIVE)) {
+      rowv[r] = 0.0;
+      continue;
+    }
     const double sc = D.sc[ro + r], gval = D.g[ro + r], d = sc * gval, y = D.y[ro + r];
     a_ysum += fabs(y);
     a_violu = fmax(a_violu, fmax(D.row_lo[ro + r] - gval, gval - D.row_hi[ro + r]));
-    const double ys = sc * y;
-    if (ys != 0.0)
-      for (int e = ep[r]; e < ep[r + 1]; ++e) {
-        const int col = ec[e];
-        if (col >= 0) atomicAdd(vecn + col, ys * Jv[e]);
-      }
+    rowv[r] = sc * y;
     if (f & CHD_ROW_EQ) {
       const double re = d - D.dL[ro + r];
       a_cviol = fmax(a_cviol, fabs(re));
@@ -233,8 +235,14 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   }
   __syncthreads();
   double a_dual = 0;
-  for (int i = tid; i < n; i += nt)
-    if (vk[i] >= 0) a_dual = fmax(a_dual, fabs(vecn[i]));
+  for (int i = tid; i < n; i += nt) {
+    double v = sf * grad[i];
+    for (int t = cptr[i]; t < cptr[i + 1]; ++t) {
+      const int e = cent[t];
+      v += rowv[erow[e]] * Jv[e];
+    }
+    if (vk[i] >= 0) a_dual = fmax(a_dual, fabs(v));
+  }
   const double ysum = chd_block_sum(a_ysum, red), zsum = chd_block_sum(a_zsum, red);
   const double cviol = chd_block_max(a_cviol, red), theta = chd_block_sum(a_theta, red);
   const double dual_inf = fmax(chd_block_max(a_dual, red), chd_block_max(a_rs, red));
@@ -299,6 +307,8 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   double* rhs_s = xs;   // [0, Np) band unknowns, [8*nbc_max, +nb) border unknowns
   for (int i = tid; i < 8 * D.nbc_max + nbp8; i += nt) rhs_s[i] = 0.0;
   __syncthreads();
+  // (a per-column gather of the right-hand side, as in section A, was measured slower than these shared-memory
+  // atomics, which overlap with the global reductions of the matrix entries)
   auto rhs_add = [&](int kk, double v) { atomicAdd(rhs_s + (kk < Na ? kk : 8 * D.nbc_max + (kk - Na)), v); };
   for (int i = tid; i < n; i += nt) {
     const int k = vk[i];

@@ -518,6 +518,9 @@ int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys
   hb.itab.assign((size_t)B * hb.tab_max, 0);
   hb.ent_ptr.assign((size_t)B * (hb.m_max + 1), 0);
   hb.ent_col.assign((size_t)B * hb.slots_max, -1);
+  hb.ent_row.assign((size_t)B * hb.slots_max, 0);
+  hb.col_ptr.assign((size_t)B * (hb.n_max + 1), 0);
+  hb.col_ent.assign((size_t)B * hb.slots_max, 0);
   hb.var_kkt.assign((size_t)B * hb.n_max, -1);
   hb.row_kkt.assign((size_t)B * hb.m_max, -1);
   hb.sets.assign((size_t)B * hb.sets_max, ChdSet{-1, 0, 0, 0, 0, 0});
@@ -565,6 +568,21 @@ int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys
     std::copy(sb.ent_ptr.begin(), sb.ent_ptr.end(), hb.ent_ptr.begin() + (size_t)i * (hb.m_max + 1));
     for (int r = sb.h.m + 1; r <= hb.m_max; ++r) hb.ent_ptr[(size_t)i * (hb.m_max + 1) + r] = sb.h.nslots;
     std::copy(sb.ent_col.begin(), sb.ent_col.end(), hb.ent_col.begin() + (size_t)i * hb.slots_max);
+    {
+      // column-oriented view of the same slots: J^T y and the right-hand side are gathered per variable on the device
+      int* erow = hb.ent_row.data() + (size_t)i * hb.slots_max;
+      int* cptr = hb.col_ptr.data() + (size_t)i * (hb.n_max + 1);
+      int* cent = hb.col_ent.data() + (size_t)i * hb.slots_max;
+      for (int r = 0; r < sb.h.m; ++r)
+        for (int e = sb.ent_ptr[r]; e < sb.ent_ptr[r + 1]; ++e) erow[e] = r;
+      std::vector<int> cnt(hb.n_max + 1, 0);
+      for (int e = 0; e < sb.h.nslots; ++e)
+        if (sb.ent_col[e] >= 0) cnt[sb.ent_col[e] + 1]++;
+      for (int v = 0; v < hb.n_max; ++v) cnt[v + 1] += cnt[v];
+      std::copy(cnt.begin(), cnt.end(), cptr);
+      for (int e = 0; e < sb.h.nslots; ++e)
+        if (sb.ent_col[e] >= 0) cent[cnt[sb.ent_col[e]]++] = e;
+    }
     std::copy(sb.var_kkt.begin(), sb.var_kkt.end(), hb.var_kkt.begin() + (size_t)i * hb.n_max);
     std::copy(sb.row_kkt.begin(), sb.row_kkt.end(), hb.row_kkt.begin() + (size_t)i * hb.m_max);
     std::copy(sb.sets.begin(), sb.sets.end(), hb.sets.begin() + (size_t)i * hb.sets_max);

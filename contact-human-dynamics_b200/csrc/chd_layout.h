@@ -24,6 +24,7 @@ struct ChdHostBatch {
   std::vector<ChdSeq> seq;
   std::vector<double> poly_T, poly_tend, node_const, par, t_dyn, t_rom, t_data, row_lo, row_hi, x0, phase_tend;
   std::vector<int> node_var, itab, ent_ptr, ent_col, var_kkt, row_kkt, row_set;
+  std::vector<int> ent_row, col_ptr, col_ent;   // row of every Jacobian slot; slots grouped by column (gathers instead of atomics)
   std::vector<ChdSet> sets;
   ChdStageCfg stage[6];
   int par_stride() const { return (18 + 3 * n_ee_max) * F_max; }
