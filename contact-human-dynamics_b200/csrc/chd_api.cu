@@ -51,7 +51,7 @@ struct chd_phys_batch {
   double* d_samples = nullptr;
   size_t smem_eval = 0, smem_kkt = 0, smem_ls = 0;
   int kcopy_blocks = 1;
-  ChdIpm* h_ipm = nullptr;  // pinned
+  ChdIpm* h_ipm = nullptr;  // host copy of the per-sequence solver state
   double* d_x0 = nullptr;
   int64_t h2d_bytes = 0;
   ChdStageDev* d_stages = nullptr;
@@ -64,9 +64,9 @@ template <class T>
 int dev_upload(chd_phys_batch* b, const std::vector<T>& v, const T** out) {
   void* p = nullptr;
   size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-  CHD_CUDA(cudaMalloc(&p, bytes));
+  CHD_CUDA(cudaMallocAsync(&p, bytes, b->stream));      // stream-ordered pool: freed blocks are reused by the next batch
   b->allocs.push_back(p);
-  if (!v.empty()) CHD_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (!v.empty()) CHD_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, b->stream));
   b->h2d_bytes += (int64_t)(v.size() * sizeof(T));
   *out = (const T*)p;
   return 0;
@@ -74,8 +74,8 @@ int dev_upload(chd_phys_batch* b, const std::vector<T>& v, const T** out) {
 template <class T>
 int dev_alloc(chd_phys_batch* b, size_t count, T** out) {
   void* p = nullptr;
-  CHD_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-  CHD_CUDA(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+  CHD_CUDA(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), b->stream));
+  CHD_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), b->stream));
   b->allocs.push_back(p);
   *out = (T*)p;
   return 0;
@@ -251,6 +251,16 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   D.Na_max = hb.Na_max, D.nb_max = hb.nb_max, D.w_max = hb.w_max, D.par_stride = hb.par_stride(), D.n_ee_max = hb.n_ee_max;
   D.fo_max = hb.fo_max, D.Ph_max = hb.Ph_max;
   CHD_CUDA(cudaStreamCreate(&b->stream));
+  {
+    // keep freed device memory in the default pool of this device (a batch object is created per solve by callers
+    // that mirror the reference's one-process-per-clip flow)
+    int dev_id = 0;
+    cudaMemPool_t pool;
+    CHD_CUDA(cudaGetDevice(&dev_id));
+    CHD_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev_id));
+    unsigned long long keep = ~0ull;
+    CHD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   CHD_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
   CHD_CUDA(cudaEventCreateWithFlags(&b->ev_kkt, cudaEventDisableTiming));
   CHD_CUDA(cudaEventCreateWithFlags(&b->ev_copy, cudaEventDisableTiming));
@@ -274,7 +284,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   AL(cost, B * 2) AL(Kwork, B * D.kstride) AL(Kbase, B * D.kstride) AL(sol, B * (size_t)(hb.Na_max + hb.nb_max)) AL(ipm, B)
 #undef AL
   if ((rc = dev_upload(b, hb.x0, (const double**)&b->d_x0))) return rc;
-  CHD_CUDA(cudaMemcpy(D.x, b->d_x0, nm * sizeof(double), cudaMemcpyDeviceToDevice));
+  CHD_CUDA(cudaMemcpyAsync(D.x, b->d_x0, nm * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
   // shared-memory budgets
   const size_t nbp8 = 8 * (size_t)D.nbt;
   b->smem_eval = (2 * (size_t)hb.n_max + CHD_THREADS) * sizeof(double);
@@ -313,22 +323,27 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   CHD_CUDA(cudaFuncSetAttribute(chd_k_kkt_gwin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_kkt));
   CHD_CUDA(cudaFuncSetAttribute(chd_k_linesearch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_ls));
   const size_t stride = 6 + 7 * (size_t)hb.n_ee_max;
-  CHD_CUDA(cudaMalloc((void**)&b->d_samples, B * hb.fo_max * stride * sizeof(double)));
-  CHD_CUDA(cudaMalloc((void**)&b->d_frames, B * sizeof(int)));
+  CHD_CUDA(cudaMallocAsync((void**)&b->d_samples, B * hb.fo_max * stride * sizeof(double), b->stream));
+  CHD_CUDA(cudaMallocAsync((void**)&b->d_frames, B * sizeof(int), b->stream));
   b->allocs.push_back(b->d_samples);
   b->allocs.push_back(b->d_frames);
-  CHD_CUDA(cudaMallocHost((void**)&b->h_ipm, B * sizeof(ChdIpm)));
-  CHD_CUDA(cudaMalloc((void**)&b->d_stages, 6 * sizeof(ChdStageDev)));
+  b->h_ipm = (ChdIpm*)std::malloc(B * sizeof(ChdIpm));   // pageable: pinned allocation / release cost up to 0.3 s per batch
+  if (!b->h_ipm) return -3;
+  CHD_CUDA(cudaMallocAsync((void**)&b->d_stages, 6 * sizeof(ChdStageDev), b->stream));
   b->allocs.push_back(b->d_stages);
   if ((rc = dev_alloc(b, 3 * B * hb.fo_max * stride, &D.snapshots))) return rc;
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
   *out = b;
   return 0;
 }
 
 void chd_phys_batch_destroy(chd_phys_batch* b) {
   if (!b) return;
-  for (void* p : b->allocs) cudaFree(p);
-  if (b->h_ipm) cudaFreeHost(b->h_ipm);
+  if (b->stream) {
+    for (void* p : b->allocs) cudaFreeAsync(p, b->stream);   // back to the pool, not to the driver (cudaFree cost up to 350 ms per batch)
+    cudaStreamSynchronize(b->stream);
+  }
+  std::free(b->h_ipm);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->ev_kkt) cudaEventDestroy(b->ev_kkt);

@@ -465,7 +465,9 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     //     warp 0 takes the pair that completes the next diagonal tile and factors it right away
     const int In = Kc + Q;
     if (In < nbc) {
-      for (int idx = tid - 32; idx < Q * 32 + nbt * 32; idx += nt - 32) {   // 16-byte chunks; warp 0 goes straight to the diagonal tile
+      // 16-byte chunks; warp 0 goes straight to the diagonal tile (dedicating two warps to the stream-in was measured
+      // slower: 482 vs 470 ms of KKT time per benchmark step)
+      for (int idx = tid - 32; idx < Q * 32 + nbt * 32; idx += nt - 32) {
         if (idx < 0) break;
         const int tile = idx >> 5, off = (idx & 31) * 2;
         if (tile < Q) {
