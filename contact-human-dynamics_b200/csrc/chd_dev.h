@@ -4,7 +4,7 @@
 #include "chd_layout.h"
 
 #define CHD_FILT_MAX 24
-#define CHD_THREADS 256
+#define CHD_THREADS 512
 #define CHD_KKT_THREADS 512
 #define CHD_CURV_MIN 1e-8   /* multiplier threshold below which y^+ Jd^T Jd is not added (same in oracle/ipm_oracle.cpp) */
 
