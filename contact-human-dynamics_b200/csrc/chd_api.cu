@@ -17,6 +17,7 @@ __global__ void chd_k_kkt(ChdDev D);
 __global__ void chd_k_kkt_gwin(ChdDev D);
 __global__ void chd_k_kcopy(ChdDev D);
 __global__ void chd_k_curv(ChdDev D);
+__global__ void chd_k_asm(ChdDev D);
 __global__ void chd_k_fp64_peak(int mode, int iters, double* sink);
 __global__ void chd_k_hess_base(ChdDev D);
 __global__ void chd_k_linesearch(ChdDev D);
@@ -149,7 +150,11 @@ int run_schedule(chd_phys_batch* b) {
       Timer t(b, KT_INIT);
       chd_k_hess_base<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
     }
-    if (it > 0) CHD_CUDA(cudaStreamWaitEvent(b->stream, b->ev_copy, 0));   // Kwork refreshed by the side stream
+    if (it > 0) {
+      CHD_CUDA(cudaStreamWaitEvent(b->stream, b->ev_copy, 0));   // Kwork refreshed by the side stream
+      chd_k_asm<<<dim3(8, B), 256, 0, b->stream>>>(b->D);     // matrix entries of the sequences that continue in their stage
+      b->launches++;
+    }
     {
       Timer t(b, KT_KKT);
       if (b->D.win_smem) chd_k_kkt<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);

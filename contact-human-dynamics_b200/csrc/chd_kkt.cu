@@ -154,6 +154,96 @@ __device__ __forceinline__ void chd_curv_rows(const ChdDev& D, int b, const ChdK
   }
 }
 
+// Assembly of the condensed KKT system of sequence b by threads t0, t0 + tstep, ...: matrix entries (do_mat; global
+// reductions into K) and / or right-hand side (rhs_s != nullptr; shared-memory atomics, [0, Np) band unknowns,
+// [8*nbc_max, +nb) border unknowns).  Narrow inequality rows (<= 12 slots: terrain, friction pyramid, height) are
+// condensed into the primal block (J^T Sigma J); wide ones (leg length) keep their multiplier as an unknown with
+// diagonal -1/Sigma, which needs 36 instead of 666 matrix updates per row.
+// (A per-column gather of the right-hand side, as in section A, was measured slower than the shared-memory atomics.)
+__device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT& K, double delta_w, double mu, double sf, double* rhs_s,
+                                             bool do_mat, int t0, int tstep) {
+  const ChdSeq* h = D.seq + b;
+  const int n = h->n, m = h->m, Na = K.Na;
+  const size_t ro = (size_t)b * D.m_max, vo = (size_t)b * D.n_max;
+  const int* rf = D.rflag + ro;
+  const int* vk = D.var_kkt + vo;
+  const int* rk = D.row_kkt + ro;
+  const int* ep = D.ent_ptr + (size_t)b * (D.m_max + 1);
+  const int* ec = D.ent_col + (size_t)b * D.slots_max;
+  const double* Jv = D.Jv + (size_t)b * D.slots_max;
+  const double* grad = D.grad + vo;
+  auto rhs_add = [&](int kk, double v) { if (rhs_s) atomicAdd(rhs_s + (kk < Na ? kk : 8 * D.nbc_max + (kk - Na)), v); };
+  auto mat_add = [&](int i, int j, double v) { if (do_mat) chd_kadd(K, i, j, v); };
+  for (int i = t0; i < n; i += tstep) {
+    const int k = vk[i];
+    if (k < 0) continue;
+    mat_add(k, k, delta_w);
+    rhs_add(k, -sf * grad[i]);
+  }
+  for (int r = t0; r < m; r += tstep) {
+    const int f = rf[r];
+    const int k = rk[r];
+    if (!(f & CHD_ROW_ACTIVE)) {
+      if (k >= 0) mat_add(k, k, -1.0);   // row of an inactive set: decoupled dummy unknown
+      continue;
+    }
+    const double sc = D.sc[ro + r];
+    const int e0 = ep[r], e1 = ep[r + 1];
+    if (k >= 0) {
+      // explicit row: equality, or wide inequality with its slack eliminated
+      double diag = -CHD_DELTA_C, rr;
+      if (f & CHD_ROW_EQ) {
+        rr = -(sc * D.g[ro + r] - D.dL[ro + r]);
+      } else {
+        const double s = D.s[ro + r];
+        const double gapL = (f & CHD_ROW_HASL) ? s - D.dL[ro + r] : 1.0, gapU = (f & CHD_ROW_HASU) ? D.dU[ro + r] - s : 1.0;
+        const double Sig = ((f & CHD_ROW_HASL) ? D.zL[ro + r] / gapL : 0.0) + ((f & CHD_ROW_HASU) ? D.zU[ro + r] / gapU : 0.0);
+        const double bvec = ((f & CHD_ROW_HASL) ? mu / gapL : 0.0) - ((f & CHD_ROW_HASU) ? mu / gapU : 0.0);
+        diag -= 1.0 / Sig;
+        rr = -(sc * D.g[ro + r] - s) + (D.y[ro + r] + bvec) / Sig;
+      }
+      mat_add(k, k, diag);
+      rhs_add(k, rr);
+      const double ys = sc * D.y[ro + r];
+      for (int e = e0; e < e1; ++e) {
+        const int col = ec[e];
+        if (col < 0) continue;
+        const int kc = vk[col];
+        if (kc < 0) continue;
+        const double jv = Jv[e];
+        if (jv == 0.0) continue;
+        mat_add(k, kc, sc * jv);
+        rhs_add(kc, -ys * jv);
+      }
+    } else {
+      // condensed narrow inequality row
+      const double s = D.s[ro + r];
+      const double gapL = (f & CHD_ROW_HASL) ? s - D.dL[ro + r] : 1.0, gapU = (f & CHD_ROW_HASU) ? D.dU[ro + r] - s : 1.0;
+      const double Sig = ((f & CHD_ROW_HASL) ? D.zL[ro + r] / gapL : 0.0) + ((f & CHD_ROW_HASU) ? D.zU[ro + r] / gapU : 0.0);
+      const double bvec = ((f & CHD_ROW_HASL) ? mu / gapL : 0.0) - ((f & CHD_ROW_HASU) ? mu / gapU : 0.0);
+      const double coef = Sig * (sc * D.g[ro + r] - s) - bvec;
+      for (int ea = e0; ea < e1; ++ea) {
+        const int ca = ec[ea];
+        if (ca < 0) continue;
+        const int ka = vk[ca];
+        if (ka < 0) continue;
+        const double va = sc * Jv[ea];
+        if (va == 0.0) continue;
+        rhs_add(ka, -va * coef);
+        if (do_mat)
+        for (int eb = e0; eb < e1; ++eb) {
+          const int cb = ec[eb];
+          if (cb < 0) continue;
+          const int kb = vk[cb];
+          if (kb < 0 || ka < kb) continue;
+          const double vb = sc * Jv[eb];
+          if (vb != 0.0) mat_add(ka, kb, Sig * va * vb);
+        }
+      }
+    }
+  }
+}
+
 // dynamic shared memory layout of chd_k_kkt (doubles):
 //   red[CHD_KKT_THREADS] | vecn[n_max] | xs[Np_max + nbp8] | cc[nbp8*nbp8] | ypan[(Q+nbt)*64] | xpan[(Q+nbt)*64] | xs2[Np_max] | dinv[16]
 //   | win[Q(Q+1)/2 * 64] | bwin[Q*nbt*64]            (the last two in global scratch when they do not fit)
@@ -307,76 +397,10 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   double* rhs_s = xs;   // [0, Np) band unknowns, [8*nbc_max, +nb) border unknowns
   for (int i = tid; i < 8 * D.nbc_max + nbp8; i += nt) rhs_s[i] = 0.0;
   __syncthreads();
-  // (a per-column gather of the right-hand side, as in section A, was measured slower than these shared-memory
-  // atomics, which overlap with the global reductions of the matrix entries)
-  auto rhs_add = [&](int kk, double v) { atomicAdd(rhs_s + (kk < Na ? kk : 8 * D.nbc_max + (kk - Na)), v); };
-  for (int i = tid; i < n; i += nt) {
-    const int k = vk[i];
-    if (k < 0) continue;
-    chd_kadd(K, k, k, delta_w);
-    rhs_add(k, -sf * grad[i]);
-  }
-  for (int r = tid; r < m; r += nt) {
-    const int f = rf[r];
-    const int k = rk[r];
-    if (!(f & CHD_ROW_ACTIVE)) {
-      if (k >= 0) chd_kadd(K, k, k, -1.0);   // row of an inactive set: decoupled dummy unknown
-      continue;
-    }
-    const double sc = D.sc[ro + r];
-    const int e0 = ep[r], e1 = ep[r + 1];
-    if (k >= 0) {
-      // explicit row: equality, or wide inequality with its slack eliminated
-      double diag = -CHD_DELTA_C, rr;
-      if (f & CHD_ROW_EQ) {
-        rr = -(sc * D.g[ro + r] - D.dL[ro + r]);
-      } else {
-        const double s = D.s[ro + r];
-        const double gapL = (f & CHD_ROW_HASL) ? s - D.dL[ro + r] : 1.0, gapU = (f & CHD_ROW_HASU) ? D.dU[ro + r] - s : 1.0;
-        const double Sig = ((f & CHD_ROW_HASL) ? D.zL[ro + r] / gapL : 0.0) + ((f & CHD_ROW_HASU) ? D.zU[ro + r] / gapU : 0.0);
-        const double bvec = ((f & CHD_ROW_HASL) ? mu / gapL : 0.0) - ((f & CHD_ROW_HASU) ? mu / gapU : 0.0);
-        diag -= 1.0 / Sig;
-        rr = -(sc * D.g[ro + r] - s) + (D.y[ro + r] + bvec) / Sig;
-      }
-      chd_kadd(K, k, k, diag);
-      rhs_add(k, rr);
-      const double ys = sc * D.y[ro + r];
-      for (int e = e0; e < e1; ++e) {
-        const int col = ec[e];
-        if (col < 0) continue;
-        const int kc = vk[col];
-        if (kc < 0) continue;
-        const double jv = Jv[e];
-        if (jv == 0.0) continue;
-        chd_kadd(K, k, kc, sc * jv);
-        rhs_add(kc, -ys * jv);
-      }
-    } else {
-      // condensed narrow inequality row
-      const double s = D.s[ro + r];
-      const double gapL = (f & CHD_ROW_HASL) ? s - D.dL[ro + r] : 1.0, gapU = (f & CHD_ROW_HASU) ? D.dU[ro + r] - s : 1.0;
-      const double Sig = ((f & CHD_ROW_HASL) ? D.zL[ro + r] / gapL : 0.0) + ((f & CHD_ROW_HASU) ? D.zU[ro + r] / gapU : 0.0);
-      const double bvec = ((f & CHD_ROW_HASL) ? mu / gapL : 0.0) - ((f & CHD_ROW_HASU) ? mu / gapU : 0.0);
-      const double coef = Sig * (sc * D.g[ro + r] - s) - bvec;
-      for (int ea = e0; ea < e1; ++ea) {
-        const int ca = ec[ea];
-        if (ca < 0) continue;
-        const int ka = vk[ca];
-        if (ka < 0) continue;
-        const double va = sc * Jv[ea];
-        if (va == 0.0) continue;
-        rhs_add(ka, -va * coef);
-        for (int eb = e0; eb < e1; ++eb) {
-          const int cb = ec[eb];
-          if (cb < 0) continue;
-          const int kb = vk[cb];
-          if (kb < 0 || ka < kb) continue;
-          const double vb = sc * Jv[eb];
-          if (vb != 0.0) chd_kadd(K, ka, kb, Sig * va * vb);
-        }
-      }
-    }
-  }
+  // matrix entries do not depend on the barrier parameter: for sequences that continue in their stage they were
+  // added by chd_k_asm (8 CTAs per sequence) before this kernel; the right-hand side (shared-memory atomics) is
+  // always assembled here
+  chd_assemble(D, b, K, delta_w, mu, sf, rhs_s, !pre_refreshed, tid, nt);
   __syncthreads();
   for (int i = tid; i < K.Np; i += nt) K.bord[((size_t)(i >> 3) * nbt + (NBR >> 3)) * 64 + (NBR & 7) * 8 + (i & 7)] = i < Na ? rhs_s[i] : 0.0;
   for (int i = tid; i < nbl; i += nt) K.corn[(size_t)NBR * nbp8 + i] = rhs_s[8 * D.nbc_max + i];
@@ -881,6 +905,18 @@ __global__ void __launch_bounds__(256) chd_k_curv(ChdDev D) {
   chd_kt_init(D, D.seq + b, D.Kwork + (size_t)b * D.kstride, K);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   chd_curv_rows(D, b, K, D.stages[I.stage], blockIdx.x * 8 + warp, gridDim.x * 8, lane, s_ws + warp * 192);
+}
+
+// matrix part of the assembly for the sequences that continue in their stage (Kwork already refreshed by chd_k_kcopy
+// and chd_k_curv): grid (G, B), launched right before chd_k_kkt.  The reductions into L2 are the cost, so G CTAs per
+// sequence on the SMs the one-CTA-per-sequence kernels leave idle take 1/G of the time.
+__global__ void __launch_bounds__(256) chd_k_asm(ChdDev D) {
+  const int b = blockIdx.y;
+  const ChdIpm& I = D.ipm[b];
+  if (!I.kw_req || I.phase != CHD_PH_RUN) return;
+  ChdKT K;
+  chd_kt_init(D, D.seq + b, D.Kwork + (size_t)b * D.kstride, K);
+  chd_assemble(D, b, K, I.delta_w, I.mu, I.sf, nullptr, true, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // fp64 throughput probe for the roofline denominators: mode 0 = DFMA chains, mode 1 = DMMA (mma.sync m8n8k4 f64)

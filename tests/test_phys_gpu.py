@@ -162,3 +162,11 @@ def test_phys_optim_cli_files(chd, tmp_path):
     r = chd.io_formats.read_solution(os.path.join(outd, "sol_out_durations.txt"))
     assert r["num_frames"] == 60 and r["num_feet"] == 2 and np.isfinite(r["foot_force"]).all()
     assert open(os.path.join(outd, "success_log.txt")).read() == "dynamics 1\ndurations 1\n"
+
+
+def test_fp64_peak_probe(chd):
+    """chd_measure_fp64_peak (roofline denominator of bench.py): DFMA and DMMA throughput of the device, both far above
+    anything a single SM could deliver and of the same order (B200: ~36-37 TFLOP/s each)."""
+    dfma, dmma = chd.phys.measure_fp64_peak()
+    assert 5e3 < dfma < 2e5 and 5e3 < dmma < 2e5
+    assert 0.3 < dfma / dmma < 3.0
