@@ -88,6 +88,12 @@ __device__ __forceinline__ bool chd_tile_ldl(double* T, double* dinv, double* wi
 #pragma unroll
   for (int c = 0; c < 8; ++c) a[c] = c <= r ? T[r * 8 + c] : 0.0;
   bool ok = true;
+  // W = L^-1 by forward substitution on the rows, w = e_r - sum_{j<r} L[r][j] W[j][:], interleaved with the
+  // elimination: column p of L is final after pivot p and row p of W after step p-1, so step p of the recurrence has no
+  // dependence on the next pivot's divide -> multiply -> fma chain and fills its latency
+  double w[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) w[c] = c == r ? 1.0 : 0.0;
 #pragma unroll
   for (int p = 0; p < 8; ++p) {
     const double dp = __shfl_sync(0xffffffffu, a[p], p, 8);
@@ -101,23 +107,18 @@ __device__ __forceinline__ bool chd_tile_ldl(double* T, double* dinv, double* wi
     }
     if (r > p) a[p] = lr;
     if (lane == p) dinv[p] = inv;
+    if (p < 7) {
+#pragma unroll
+      for (int c = 0; c <= p; ++c) {
+        const double wpc = __shfl_sync(0xffffffffu, w[c], p, 8);
+        if (r > p) w[c] -= lr * wpc;
+      }
+    }
   }
   if (lane < 8) {
 #pragma unroll
     for (int c = 0; c < 8; ++c)
       if (c <= r) T[r * 8 + c] = a[c];
-  }
-  // W = L^-1 by forward substitution on the rows: w = e_r - sum_{j<r} L[r][j] W[j][:], row j is final at step j
-  double w[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) w[c] = c == r ? 1.0 : 0.0;
-#pragma unroll
-  for (int j = 0; j < 7; ++j) {
-#pragma unroll
-    for (int c = 0; c <= j; ++c) {
-      const double wjc = __shfl_sync(0xffffffffu, w[c], j, 8);
-      if (r > j) w[c] -= a[j] * wjc;
-    }
   }
   if (lane < 8) {
 #pragma unroll
