@@ -429,7 +429,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   __shared__ int s_rs[2][96];
   __shared__ int s_gnz[2][96];   // per panel group: any non-zero entry in the X tile (zero tiles skip their trailing updates)
   __shared__ unsigned short s_pairs[3000];
-  __shared__ unsigned char s_cmp[CHD_KKT_THREADS / 32][32];
+  __shared__ unsigned char s_cmp[CHD_KKT_THREADS / 32][64];   // per warp: rank -> id of the non-zero panel groups
   __shared__ __align__(16) double s_winv[2][64];   // inverse of the current / next diagonal tile factor, fragment order
   const int GB = K.q, Gm = K.q + nbt, npairs = Gm * (Gm + 1) / 2;
   for (int p = tid; p < npairs && p < 3000; p += nt) {
@@ -523,20 +523,25 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       // compact list of the groups with a non-zero X tile (every warp builds it redundantly: no extra barrier).
       // the pair table enumerates (i >= j) row by row, so its first na(na+1)/2 entries pair the first na entries.
       const int* gnz = s_gnz[cur];
-      int myg = -1, na;
+      int na;
+      const unsigned char* cmp = s_cmp[warp];
       {
-        const bool act = lane < Gm && (lane >= GB || lane < tq) && gnz[lane];
-        const unsigned msk = __ballot_sync(0xffffffffu, act);
-        na = __popc(msk);
-        // lane l receives the id of the l-th active group (scatter by rank through a per-warp table; __fns is slow)
-        if (act) s_cmp[warp][__popc(msk & ((1u << lane) - 1u))] = (unsigned char)lane;
+        // up to 64 groups, two per lane; scatter by rank through a per-warp table (__fns is slow)
+        const int g1 = lane + 32;
+        const bool act0 = lane < Gm && (lane >= GB || lane < tq) && gnz[lane];
+        const bool act1 = g1 < Gm && (g1 >= GB || g1 < tq) && gnz[g1 < 96 ? g1 : 0];
+        const unsigned m0 = __ballot_sync(0xffffffffu, act0), m1 = __ballot_sync(0xffffffffu, act1);
+        const unsigned below = (1u << lane) - 1u;
+        const int n0 = __popc(m0);
+        na = n0 + __popc(m1);
+        if (act0) s_cmp[warp][__popc(m0 & below)] = (unsigned char)lane;
+        if (act1) s_cmp[warp][n0 + __popc(m1 & below)] = (unsigned char)g1;
         __syncwarp();
-        myg = lane < na ? (int)s_cmp[warp][lane] : -1;
       }
-      const bool compact = Gm <= 32;
+      const bool compact = Gm <= 64;
       const int np_loop = compact ? na * (na + 1) / 2 : npairs;
-      if (!WS) {
-        // window in global (L2) memory: each warp collects up to four target tiles, issues all their loads, and only
+      if (!WS && !compact) {
+        // more than 64 panel groups, window in global (L2) memory: each warp collects up to four target tiles, issues all their loads, and only
         // then runs the tensor-core updates and the stores.  (With the window in shared memory the simple loop below
         // is faster: measured 707 vs 820 ms of KKT time per benchmark step.)
         const int r8 = (lane >> 2) * 8 + 2 * (lane & 3);
@@ -550,7 +555,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
             p += nwarp - 1;
             int gi, gj;
             if (compact) {
-              gi = __shfl_sync(0xffffffffu, myg, ai), gj = __shfl_sync(0xffffffffu, myg, aj);
+              gi = cmp[ai], gj = cmp[aj];
             } else {
               gi = ai, gj = aj;
               if ((gi < GB && gi >= tq) || (gj < GB && gj >= tq) || !gnz[gi] || !gnz[gj]) continue;
@@ -591,7 +596,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
           const int ai = s_pairs[p] >> 8, aj = s_pairs[p] & 255;
           int gi, gj;
           if (compact) {
-            gi = __shfl_sync(0xffffffffu, myg, ai), gj = __shfl_sync(0xffffffffu, myg, aj);
+            gi = cmp[ai], gj = cmp[aj];
           } else {
             gi = ai, gj = aj;
             if ((gi < GB && gi >= tq) || (gj < GB && gj >= tq) || !gnz[gi] || !gnz[gj]) return 0;
@@ -630,8 +635,8 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
             const int i1 = 2 * bi + 1, j1 = 2 * bj + 1;
             const bool vi1 = i1 < na, vj1 = j1 < na;
             int gi[2], gj[2];
-            gi[0] = __shfl_sync(0xffffffffu, myg, 2 * bi), gi[1] = __shfl_sync(0xffffffffu, myg, i1 & 31);
-            gj[0] = __shfl_sync(0xffffffffu, myg, 2 * bj), gj[1] = __shfl_sync(0xffffffffu, myg, j1 & 31);
+            gi[0] = cmp[2 * bi], gi[1] = cmp[i1 & 63];
+            gj[0] = cmp[2 * bj], gj[1] = cmp[j1 & 63];
             double2 xf[2], yf[2];
             xf[0] = *reinterpret_cast<const double2*>(xpan + gi[0] * 64 + 2 * lane);
             yf[0] = *reinterpret_cast<const double2*>(ypan + gj[0] * 64 + 2 * lane);
