@@ -415,13 +415,16 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   // ---------------- C. tiled band LDL^T with dense border ----------------
   // corner (incl. rhs row) to shared memory; initial window: band tiles (I, J), 0 <= J <= I <= q and border columns 0..q
   for (int i = tid; i < nbp8 * nbp8; i += nt) cc[i] = K.corn[i];
-  for (int idx = tid; idx < Q * Q * 64; idx += nt) {
-    const int e = idx & 63, pr = idx >> 6, J = pr / Q, t = pr % Q;
-    if (J + t < Q && J < nbc && J + t < nbc) win[chd_win_slot(J + t, J, Q) * 64 + e] = K.band[((size_t)J * Q + t) * 64 + e];
-  }
-  for (int idx = tid; idx < Q * nbt * 64; idx += nt) {
-    const int J = idx / (nbt * 64);
-    if (J < nbc) bwin[idx] = K.bord[(size_t)J * nbt * 64 + idx % (nbt * 64)];
+  // (without the shared-memory window the factorisation runs in place on Kwork: no window copy, no stream-in)
+  if (WS) {
+    for (int idx = tid; idx < Q * Q * 64; idx += nt) {
+      const int e = idx & 63, pr = idx >> 6, J = pr / Q, t = pr % Q;
+      if (J + t < Q && J < nbc && J + t < nbc) win[chd_win_slot(J + t, J, Q) * 64 + e] = K.band[((size_t)J * Q + t) * 64 + e];
+    }
+    for (int idx = tid; idx < Q * nbt * 64; idx += nt) {
+      const int J = idx / (nbt * 64);
+      if (J < nbc) bwin[idx] = K.bord[(size_t)J * nbt * 64 + idx % (nbt * 64)];
+    }
   }
   __syncthreads();
   // index tables: pair list (gi >= gj) over band groups 0..q-1 and border groups q..q+nbt-1 (built once),
@@ -442,7 +445,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   for (int g = tid; g < GB; g += nt) s_rs[0][g] = (1 + g) % Q;
   for (int g = tid; g < 96; g += nt) s_gnz[0][g] = 0, s_gnz[1][g] = 0;
   if (warp == 0) {
-    const bool ok = chd_tile_ldl(win, dinv, s_winv[0], lane);   // tile (0,0) sits in slot 0
+    const bool ok = chd_tile_ldl(WS ? win : K.band, dinv, s_winv[0], lane);   // tile (0,0) sits in slot 0
     if (!ok && lane == 0) s_fail = 1;
   }
   __syncthreads();
@@ -450,8 +453,15 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   for (int Kc = 0; Kc < nbc; ++Kc, cur ^= 1) {
     const int tq = min(K.q, nbc - 1 - Kc);          // band tiles below the diagonal tile
     const int* rs = s_rs[cur];
-    double* Tkk = win + (size_t)tri(kslot, kslot) * 64;
-    double* Bk = bwin + (size_t)kslot * nbt * 64;
+    // tile addresses: circular triangular window in shared memory, or in place in the global band / border storage
+    auto band_tile = [&](int gi, int gj) -> double* {     // tile (Kc+1+gi, Kc+1+gj), gi >= gj
+      return WS ? win + (size_t)tri(rs[gi], rs[gj]) * 64 : K.band + ((size_t)(Kc + 1 + gj) * Q + (gi - gj)) * 64;
+    };
+    auto bord_tile = [&](int bi, int gj) -> double* {     // border tile bi of block column Kc+1+gj
+      return WS ? bwin + ((size_t)rs[gj] * nbt + bi) * 64 : K.bord + ((size_t)(Kc + 1 + gj) * nbt + bi) * 64;
+    };
+    double* Tkk = WS ? win + (size_t)tri(kslot, kslot) * 64 : K.band + (size_t)Kc * Q * 64;
+    double* Bk = WS ? bwin + (size_t)kslot * nbt * 64 : K.bord + (size_t)Kc * nbt * 64;
     const double* dv = dinv + 8 * cur;
     // (b) panel: Y = A L0^-T = A W^T (W = L0^-1 from the diagonal-tile factorisation) as one tensor-core product per
     //     8x8 panel tile, X = Y D^-1; both go to the panel buffers in fragment order, X also to global (final L);
@@ -465,7 +475,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       for (int g = warp; g < tq + nbt; g += nwarp) {
         const bool band_t = g < tq;
         const int pg = band_t ? g : GB + (g - tq);                   // group id inside the panel buffers
-        const double* A = band_t ? win + (size_t)tri(rs[g], kslot) * 64 : Bk + (g - tq) * 64;
+        const double* A = band_t ? (WS ? win + (size_t)tri(rs[g], kslot) * 64 : K.band + ((size_t)Kc * Q + 1 + g) * 64) : Bk + (g - tq) * 64;
         const double ax = A[r * 8 + k], ay = A[r * 8 + k + 4];
         double c0 = 0.0, c1 = 0.0;
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -483,12 +493,13 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
         if (lane == 0 && nz) s_gnz[cur][pg] = 1;
       }
     }
-    for (int e = tid; e < 64; e += nt) K.band[(size_t)Kc * Q * 64 + e] = Tkk[e];
+    if (WS)
+      for (int e = tid; e < 64; e += nt) K.band[(size_t)Kc * Q * 64 + e] = Tkk[e];
     __syncthreads();
     // (c) stream in block row Kc + Q (its slots are dead now), trailing updates on the fp64 tensor core;
     //     warp 0 takes the pair that completes the next diagonal tile and factors it right away
     const int In = Kc + Q;
-    if (In < nbc) {
+    if (WS && In < nbc) {
       // 16-byte chunks; warp 0 goes straight to the diagonal tile (dedicating two warps to the stream-in was measured
       // slower: 482 vs 470 ms of KKT time per benchmark step)
       for (int idx = tid - 32; idx < Q * 32 + nbt * 32; idx += nt - 32) {
@@ -505,7 +516,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     }
     if (warp == 0) {
       if (tq >= 1) {
-        double* Tn = win + (size_t)tri(rs[0], rs[0]) * 64;
+        double* Tn = band_tile(0, 0);
         chd_tile_sub_xyT(Tn, xpan, ypan, lane);
         __syncwarp();
         const bool ok = chd_tile_ldl(Tn, dinv + 8 * (cur ^ 1), s_winv[cur ^ 1], lane);
@@ -564,9 +575,9 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
             const double* X = xpan + gi * 64;
             const double* Y = ypan + gj * 64;
             if (gi < GB) {
-              Cp[nq] = win + (size_t)tri(rs[gi], rs[gj]) * 64, Xp[nq] = X, Yp[nq] = Y, ++nq;
+              Cp[nq] = band_tile(gi, gj), Xp[nq] = X, Yp[nq] = Y, ++nq;
             } else if (gj < GB) {
-              Cp[nq] = bwin + ((size_t)rs[gj] * nbt + (gi - GB)) * 64, Xp[nq] = X, Yp[nq] = Y, ++nq;
+              Cp[nq] = bord_tile(gi - GB, gj), Xp[nq] = X, Yp[nq] = Y, ++nq;
             } else {
               const int bi = gi - GB, bj = gj - GB;
               for (int e = lane; e < 64; e += 32) {
@@ -605,11 +616,11 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
           X = xpan + gi * 64;
           Y = ypan + gj * 64;
           if (gi < GB) {
-            C = win + (size_t)tri(rs[gi], rs[gj]) * 64;
+            C = band_tile(gi, gj);
             return 1;
           }
           if (gj < GB) {
-            C = bwin + ((size_t)rs[gj] * nbt + (gi - GB)) * 64;
+            C = bord_tile(gi - GB, gj);
             return 1;
           }
           bi = gi - GB, bj = gj - GB;
@@ -652,8 +663,8 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
               ok = ok && !(g_i == 0 && g_j == 0);       // the next diagonal tile is updated by warp 0
               Cp[t] = nullptr;
               if (ok) {
-                if (g_i < GB) Cp[t] = win + (size_t)tri(rs[g_i], rs[g_j]) * 64;
-                else if (g_j < GB) Cp[t] = bwin + ((size_t)rs[g_j] * nbt + (g_i - GB)) * 64;
+                if (g_i < GB) Cp[t] = band_tile(g_i, g_j);
+                else if (g_j < GB) Cp[t] = bord_tile(g_i - GB, g_j);
                 else corner(xpan + g_i * 64, ypan + g_j * 64, g_i - GB, g_j - GB);
               }
               if (Cp[t]) cv[t] = *reinterpret_cast<const double2*>(Cp[t] + r8);
