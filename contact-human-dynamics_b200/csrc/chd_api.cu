@@ -287,6 +287,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   D.kstride = (size_t)D.nbc_max * D.Q * 64 + (size_t)D.nbc_max * D.nbt * 64 + (size_t)64 * D.nbt * D.nbt;
   b->kcopy_blocks = (int)std::min<size_t>(512, std::max<size_t>(std::max<size_t>(1, 592 / B), D.kstride * sizeof(double) / 131072));
   AL(cost, B * 2) AL(Kwork, B * D.kstride) AL(Kbase, B * D.kstride) AL(sol, B * (size_t)(hb.Na_max + hb.nb_max)) AL(ipm, B)
+  AL(rhs0, B * (size_t)(hb.Na_max + hb.nb_max)) AL(rhs1, B * (size_t)(hb.Na_max + hb.nb_max))
 #undef AL
   if ((rc = dev_upload(b, hb.x0, (const double**)&b->d_x0))) return rc;
   CHD_CUDA(cudaMemcpyAsync(D.x, b->d_x0, nm * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));

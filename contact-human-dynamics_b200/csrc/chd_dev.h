@@ -63,6 +63,7 @@ struct ChdDev {
   double* Kbase;                              // B x kstride  per-stage constant part (Gauss-Newton cost Hessian)
   double* sol;                                // B x (Na_max + nb_max)
   double* scratch;                            // per-sequence vectors + elimination window when they do not fit in shared memory
+  double *rhs0, *rhs1;                        // right-hand side of the KKT system as rhs0 + mu * rhs1 (chd_k_asm), [B][Na_max + nb_max]
   size_t scratch_stride;                      // doubles per sequence in `scratch`
   ChdIpm* ipm;                                // B
   const ChdStageDev* stages;                  // 6 stage configurations (device)

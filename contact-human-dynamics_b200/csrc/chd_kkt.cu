@@ -160,8 +160,10 @@ __device__ __forceinline__ void chd_curv_rows(const ChdDev& D, int b, const ChdK
 // condensed into the primal block (J^T Sigma J); wide ones (leg length) keep their multiplier as an unknown with
 // diagonal -1/Sigma, which needs 36 instead of 666 matrix updates per row.
 // (A per-column gather of the right-hand side, as in section A, was measured slower than the shared-memory atomics.)
+// g0 / g1 (global, chd_k_asm): the right-hand side split as rhs = g0 + mu * g1 -- every term is affine in the barrier
+// parameter, which is only decided inside chd_k_kkt -- accumulated with global reductions.
 __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT& K, double delta_w, double mu, double sf, double* rhs_s,
-                                             bool do_mat, int t0, int tstep) {
+                                             bool do_mat, int t0, int tstep, double* g0 = nullptr, double* g1 = nullptr) {
   const ChdSeq* h = D.seq + b;
   const int n = h->n, m = h->m, Na = K.Na;
   const size_t ro = (size_t)b * D.m_max, vo = (size_t)b * D.n_max;
@@ -174,11 +176,19 @@ __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT
   const double* grad = D.grad + vo;
   auto rhs_add = [&](int kk, double v) { if (rhs_s) atomicAdd(rhs_s + (kk < Na ? kk : 8 * D.nbc_max + (kk - Na)), v); };
   auto mat_add = [&](int i, int j, double v) { if (do_mat) chd_kadd(K, i, j, v); };
+  auto gidx = [&](int kk) { return kk < Na ? kk : D.Na_max + (kk - Na); };
+  auto g_add = [&](int kk, double v0, double v1) {
+    if (g0) {
+      atomicAdd(g0 + gidx(kk), v0);
+      if (v1 != 0.0) atomicAdd(g1 + gidx(kk), v1);
+    }
+  };
   for (int i = t0; i < n; i += tstep) {
     const int k = vk[i];
     if (k < 0) continue;
     mat_add(k, k, delta_w);
     rhs_add(k, -sf * grad[i]);
+    g_add(k, -sf * grad[i], 0.0);
   }
   for (int r = t0; r < m; r += tstep) {
     const int f = rf[r];
@@ -191,9 +201,10 @@ __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT
     const int e0 = ep[r], e1 = ep[r + 1];
     if (k >= 0) {
       // explicit row: equality, or wide inequality with its slack eliminated
-      double diag = -CHD_DELTA_C, rr;
+      double diag = -CHD_DELTA_C, rr, rr0, rr1 = 0.0;
       if (f & CHD_ROW_EQ) {
         rr = -(sc * D.g[ro + r] - D.dL[ro + r]);
+        rr0 = rr;
       } else {
         const double s = D.s[ro + r];
         const double gapL = (f & CHD_ROW_HASL) ? s - D.dL[ro + r] : 1.0, gapU = (f & CHD_ROW_HASU) ? D.dU[ro + r] - s : 1.0;
@@ -201,9 +212,12 @@ __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT
         const double bvec = ((f & CHD_ROW_HASL) ? mu / gapL : 0.0) - ((f & CHD_ROW_HASU) ? mu / gapU : 0.0);
         diag -= 1.0 / Sig;
         rr = -(sc * D.g[ro + r] - s) + (D.y[ro + r] + bvec) / Sig;
+        rr0 = -(sc * D.g[ro + r] - s) + D.y[ro + r] / Sig;
+        rr1 = (((f & CHD_ROW_HASL) ? 1.0 / gapL : 0.0) - ((f & CHD_ROW_HASU) ? 1.0 / gapU : 0.0)) / Sig;
       }
       mat_add(k, k, diag);
       rhs_add(k, rr);
+      g_add(k, rr0, rr1);
       const double ys = sc * D.y[ro + r];
       for (int e = e0; e < e1; ++e) {
         const int col = ec[e];
@@ -214,6 +228,7 @@ __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT
         if (jv == 0.0) continue;
         mat_add(k, kc, sc * jv);
         rhs_add(kc, -ys * jv);
+        g_add(kc, -ys * jv, 0.0);
       }
     } else {
       // condensed narrow inequality row
@@ -222,6 +237,8 @@ __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT
       const double Sig = ((f & CHD_ROW_HASL) ? D.zL[ro + r] / gapL : 0.0) + ((f & CHD_ROW_HASU) ? D.zU[ro + r] / gapU : 0.0);
       const double bvec = ((f & CHD_ROW_HASL) ? mu / gapL : 0.0) - ((f & CHD_ROW_HASU) ? mu / gapU : 0.0);
       const double coef = Sig * (sc * D.g[ro + r] - s) - bvec;
+      const double coef0 = Sig * (sc * D.g[ro + r] - s);
+      const double beta = ((f & CHD_ROW_HASL) ? 1.0 / gapL : 0.0) - ((f & CHD_ROW_HASU) ? 1.0 / gapU : 0.0);
       for (int ea = e0; ea < e1; ++ea) {
         const int ca = ec[ea];
         if (ca < 0) continue;
@@ -230,6 +247,7 @@ __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT
         const double va = sc * Jv[ea];
         if (va == 0.0) continue;
         rhs_add(ka, -va * coef);
+        g_add(ka, -va * coef0, va * beta);
         if (do_mat)
         for (int eb = e0; eb < e1; ++eb) {
           const int cb = ec[eb];
@@ -400,7 +418,14 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   // matrix entries do not depend on the barrier parameter: for sequences that continue in their stage they were
   // added by chd_k_asm (8 CTAs per sequence) before this kernel; the right-hand side (shared-memory atomics) is
   // always assembled here
-  chd_assemble(D, b, K, delta_w, mu, sf, rhs_s, !pre_refreshed, tid, nt);
+  if (pre_refreshed) {
+    const double* r0 = D.rhs0 + (size_t)b * (D.Na_max + D.nb_max);
+    const double* r1 = D.rhs1 + (size_t)b * (D.Na_max + D.nb_max);
+    for (int i = tid; i < Na; i += nt) rhs_s[i] = r0[i] + mu * r1[i];
+    for (int i = tid; i < nbl; i += nt) rhs_s[8 * D.nbc_max + i] = r0[D.Na_max + i] + mu * r1[D.Na_max + i];
+  } else {
+    chd_assemble(D, b, K, delta_w, mu, sf, rhs_s, true, tid, nt);
+  }
   __syncthreads();
   for (int i = tid; i < K.Np; i += nt) K.bord[((size_t)(i >> 3) * nbt + (NBR >> 3)) * 64 + (NBR & 7) * 8 + (i & 7)] = i < Na ? rhs_s[i] : 0.0;
   for (int i = tid; i < nbl; i += nt) K.corn[(size_t)NBR * nbp8 + i] = rhs_s[8 * D.nbc_max + i];
@@ -897,6 +922,10 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
 __global__ void __launch_bounds__(256) chd_k_kcopy(ChdDev D) {
   const int b = blockIdx.y;
   if (!D.ipm[b].kw_req) return;
+  if (blockIdx.x == 0) {   // right-hand side accumulators of chd_k_asm
+    const size_t go = (size_t)b * (D.Na_max + D.nb_max);
+    for (int i = threadIdx.x; i < D.Na_max + D.nb_max; i += blockDim.x) D.rhs0[go + i] = 0.0, D.rhs1[go + i] = 0.0;
+  }
   const size_t cnt2 = D.kstride / 2, per = (cnt2 + gridDim.x - 1) / gridDim.x;
   const size_t lo = (size_t)blockIdx.x * per, hi = lo + per < cnt2 ? lo + per : cnt2;
   const double2* src = reinterpret_cast<const double2*>(D.Kbase + (size_t)b * D.kstride);
@@ -932,7 +961,8 @@ __global__ void __launch_bounds__(256) chd_k_asm(ChdDev D) {
   if (!I.kw_req || I.phase != CHD_PH_RUN) return;
   ChdKT K;
   chd_kt_init(D, D.seq + b, D.Kwork + (size_t)b * D.kstride, K);
-  chd_assemble(D, b, K, I.delta_w, I.mu, I.sf, nullptr, true, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+  const size_t go = (size_t)b * (D.Na_max + D.nb_max);
+  chd_assemble(D, b, K, I.delta_w, I.mu, I.sf, nullptr, true, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, D.rhs0 + go, D.rhs1 + go);
 }
 
 // fp64 throughput probe for the roofline denominators: mode 0 = DFMA chains, mode 1 = DMMA (mma.sync m8n8k4 f64)
