@@ -651,14 +651,11 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
           bi = gi - GB, bj = gj - GB;
           return 2;
         };
-        auto corner = [&](const double* X, const double* Y, int bi, int bj) {   // corner block: strided rows, scalar code
-          for (int e = lane; e < 64; e += 32) {
-            const int r = e >> 3, cq = e & 7;
-            double acc = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) acc += X[r * 8 + kk] * Y[cq * 8 + kk];
-            cc[(bi * 8 + r) * nbp8 + bj * 8 + cq] -= acc;
-          }
+        auto corner = [&](const double* X, const double* Y, int bi, int bj) {   // corner block: same tensor-core update, row stride nbp8
+          double* Cc = cc + (size_t)(bi * 8 + (lane >> 2)) * nbp8 + bj * 8 + 2 * (lane & 3);
+          double c0 = Cc[0], c1 = Cc[1];
+          chd_tile_mma(c0, c1, X, Y, lane);
+          Cc[0] = c0, Cc[1] = c1;
         };
         const int step = nwarp - 1, r8 = (lane >> 2) * 8 + 2 * (lane & 3);
         if (compact) {
