@@ -758,11 +758,17 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     __syncthreads();
   }
   double* xb = xs + 8 * D.nbc_max;  // border solution
-  if (tid == 0) {
+  if (warp == 0) {
+    // column-oriented back-substitution by one warp: x_k = acc_k / d_k, then acc_j -= (L d)[k][j] x_k for j < k
+    // (row k of cc holds the unscaled column entries; one division per unknown instead of one per matrix entry)
+    for (int j = lane; j < nbl; j += 32) xb[j] = cc[NBR * nbp8 + j];
+    __syncwarp();
     for (int k = nbl - 1; k >= 0; --k) {
-      double v = cc[NBR * nbp8 + k] / cc[k * nbp8 + k];
-      for (int i = k + 1; i < nbl; ++i) v -= (cc[i * nbp8 + k] / cc[k * nbp8 + k]) * xb[i];
-      xb[k] = v;
+      const double xk = xb[k] / cc[k * nbp8 + k];
+      __syncwarp();
+      for (int j = lane; j < k; j += 32) xb[j] -= cc[k * nbp8 + j] * xk;
+      if (lane == 0) xb[k] = xk;
+      __syncwarp();
     }
   }
   __syncthreads();
