@@ -1,13 +1,18 @@
 // KKT kernels of the batched interior-point solver (product code, sm_100a).
 //
 //   chd_k_hess_base : once per stage -- Gauss-Newton Hessian of the (quadratic, fixed-duration) cost terms
-//                     of data_cost.cpp / vel_smooth_cost.cpp, scaled by the objective scaling, in tile format
-//   chd_k_kkt       : per iteration -- IPOPT error measures + barrier update, condensed KKT assembly
-//                     (copy of the base + Jacobian dependent parts), tiled band LDL^T with dense border
-//                     (shared-memory window, FP64 tensor-core trailing updates), triangular solves,
-//                     step recovery and fraction-to-the-boundary rule
-// One CTA per sequence.  Replaces IPOPT's per-iteration MA57 factorisation (phys_optim.cpp:573) for the
-// block-banded systems this NLP produces.
+//                     of data_cost.cpp / vel_smooth_cost.cpp, scaled by the objective scaling, in tile format (Kbase)
+//   chd_k_kcopy     : per iteration, side stream -- Kwork <- Kbase for the sequences that continue in their stage
+//   chd_k_curv      : per iteration, side stream, after the line search -- y+ Jd^T Jd of the squared-distance rows
+//   chd_k_asm       : per iteration, right before chd_k_kkt -- Jacobian dependent matrix entries and the right-hand
+//                     side as rhs0 + mu * rhs1 (several CTAs per sequence: the cost is the L2 reductions)
+//   chd_k_kkt       : per iteration, one CTA per sequence -- IPOPT error measures + barrier update, (first iteration
+//                     of a stage: the whole assembly), tiled band LDL^T with dense border (shared-memory window or,
+//                     for wide bands, in place on Kwork; panel, trailing and corner updates on the FP64 tensor
+//                     core), triangular solves, step recovery and fraction-to-the-boundary rule
+//   chd_k_fp64_peak : DFMA / DMMA throughput probe for the roofline denominators of bench.py
+// Replaces IPOPT's per-iteration MA57 factorisation (phys_optim.cpp:573) for the block-banded systems this NLP
+// produces.
 #include <cuda_runtime.h>
 
 #include "chd_block.cuh"
