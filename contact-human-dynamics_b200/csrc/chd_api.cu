@@ -431,6 +431,15 @@ int chd_phys_get_layout(const chd_phys_batch* b, int32_t* ent_ptr, int32_t* ent_
   return 0;
 }
 
+int chd_phys_get_slot_index(const chd_phys_batch* b, int32_t* ent_row, int32_t* col_ptr, int32_t* col_ent) {
+  if (!b) return -1;
+  const ChdHostBatch& hb = b->hb;
+  if (ent_row) std::memcpy(ent_row, hb.ent_row.data(), hb.ent_row.size() * sizeof(int));
+  if (col_ptr) std::memcpy(col_ptr, hb.col_ptr.data(), hb.col_ptr.size() * sizeof(int));
+  if (col_ent) std::memcpy(col_ent, hb.col_ent.data(), hb.col_ent.size() * sizeof(int));
+  return 0;
+}
+
 int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int32_t* status, int32_t* iters, double* stats) {
   if (!b || stage < 0 || stage > 5 || b->host_only) return -1;
   const int B = b->hb.B;

@@ -49,7 +49,7 @@ class _Dims(C.Structure):
 EXPORTS = ["chd_version", "chd_phys_batch_create", "chd_phys_batch_destroy", "chd_phys_get_dims", "chd_phys_get_sizes",
            "chd_phys_get_x", "chd_phys_set_x", "chd_phys_eval", "chd_phys_get_layout", "chd_phys_solve_stage",
            "chd_phys_solve", "chd_phys_sample", "chd_phys_sample_device", "chd_phys_launch_count",
-           "chd_phys_kernel_times", "chd_phys_set_timing", "chd_phys_h2d_bytes", "chd_phys_reset", "chd_measure_fp64_peak"]
+           "chd_phys_kernel_times", "chd_phys_set_timing", "chd_phys_h2d_bytes", "chd_phys_reset", "chd_measure_fp64_peak", "chd_phys_get_slot_index"]
 
 
 def measure_fp64_peak():
@@ -184,6 +184,14 @@ class PhysBatch:
                    row_kkt=np.zeros((B, d["m_max"]), np.int32))
         self._chk(self.L.chd_phys_get_layout(self.h, *[_ptr(out[k]) for k in ("ent_ptr", "ent_col", "row_lo", "row_hi",
                                                                               "row_set", "var_kkt", "row_kkt")]))
+        return out
+
+    def slot_index(self) -> dict:
+        """Column-oriented view of the Jacobian slots: ent_row (B,slots_max), col_ptr (B,n_max+1), col_ent (B,slots_max)."""
+        B, d = self.B, self.dims
+        out = dict(ent_row=np.zeros((B, d["slots_max"]), np.int32), col_ptr=np.zeros((B, d["n_max"] + 1), np.int32),
+                   col_ent=np.zeros((B, d["slots_max"]), np.int32))
+        self._chk(self.L.chd_phys_get_slot_index(self.h, *[_ptr(out[k]) for k in ("ent_row", "col_ptr", "col_ent")]))
         return out
 
     def eval(self, stage) -> dict:

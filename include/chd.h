@@ -83,6 +83,10 @@ int chd_phys_eval(chd_phys_batch* b, int32_t stage, double* cost, double* grad, 
  *   var_kkt[batch x n_max], row_kkt[batch x m_max] (KKT ordering; -1 = not an unknown). */
 int chd_phys_get_layout(const chd_phys_batch* b, int32_t* ent_ptr, int32_t* ent_col, double* row_lo, double* row_hi,
                         int32_t* row_set, int32_t* var_kkt, int32_t* row_kkt);
+/* Column-oriented view of the same Jacobian slots (what ifopt keeps as a column-compressed Eigen matrix,
+ * ifopt::Composite::GetJacobian): ent_row[batch x slots_max] (row of every slot), col_ptr[batch x (n_max+1)],
+ * col_ent[batch x slots_max] (slots grouped by variable).  [host] outputs, any may be NULL. */
+int chd_phys_get_slot_index(const chd_phys_batch* b, int32_t* ent_row, int32_t* col_ptr, int32_t* col_ent);
 
 /* Runs the interior-point solve of one stage for every sequence (warm start from the current x).
  * status[batch] [host]: 0 = converged (IPOPT "Solve_Succeeded" test), -1 = iteration cap, -2 = numerical failure.

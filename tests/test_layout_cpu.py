@@ -73,3 +73,23 @@ def test_library_exports(chd):
     declared = set(re.findall(r"\b(chd_[a-z_0-9]+)\s*\(", hdr))
     for name in declared:
         assert hasattr(L, name), "declared in include/chd.h but not exported: " + name
+
+
+def test_column_oriented_slot_index(chd):
+    """ent_row / col_ptr / col_ent (used by the device to gather J^T y per variable) describe exactly the slots of
+    ent_ptr / ent_col: every slot with a variable appears once, under its own column, with its own row."""
+    ps = [chd.synth.make_problem(s, n_ee=ne) for s, ne in ((0, 2), (3, 4))]
+    b = chd.phys.PhysBatch(ps, host_only=True)
+    lay, idx = b.layout(), b.slot_index()
+    for i in range(len(ps)):
+        n, m, nslots = (int(v) for v in b.sizes[i, :3])
+        ep, ec = lay["ent_ptr"][i], lay["ent_col"][i]
+        er, cp, ce = idx["ent_row"][i], idx["col_ptr"][i], idx["col_ent"][i]
+        for r in range(m):
+            assert (er[ep[r]:ep[r + 1]] == r).all()
+        assert cp[0] == 0 and (np.diff(cp[:n + 1]) >= 0).all()
+        used = np.flatnonzero(ec[:nslots] >= 0)
+        assert cp[n] == len(used)
+        assert sorted(ce[:cp[n]].tolist()) == used.tolist()
+        for v in range(n):
+            assert (ec[ce[cp[v]:cp[v + 1]]] == v).all()
