@@ -93,3 +93,18 @@ def test_column_oriented_slot_index(chd):
         assert sorted(ce[:cp[n]].tolist()) == used.tolist()
         for v in range(n):
             assert (ec[ce[cp[v]:cp[v + 1]]] == v).all()
+
+
+def test_adaptive_band_border_split(chd):
+    """The layout builder chooses per sequence which stance variables go to the dense border: walking gaits keep
+    a border of a few dozen columns, densely switching contacts (0.13-0.33 s stances) fit in the band."""
+    walk = chd.phys.PhysBatch([chd.synth.make_problem(0, n_ee=2)], host_only=True).dims
+    dense = chd.phys.PhysBatch([chd.synth.make_problem(0, n_frames=300, n_ee=4, dense=True)], host_only=True).dims
+    assert 12 <= walk["nb_max"] <= 60 and walk["w_max"] <= 160
+    assert dense["nb_max"] <= 40 and dense["w_max"] <= 400
+    # every KKT unknown index is used exactly once (band + border)
+    b = chd.phys.PhysBatch([chd.synth.make_problem(1, n_frames=150, n_ee=4, dense=True)], host_only=True)
+    lay = b.layout()
+    Na, nb = int(b.sizes[0, 3]), int(b.sizes[0, 4])
+    ks = np.concatenate([lay["var_kkt"][0][lay["var_kkt"][0] >= 0], lay["row_kkt"][0][lay["row_kkt"][0] >= 0]])
+    assert sorted(ks.tolist()) == list(range(Na + nb))
