@@ -14,6 +14,7 @@
 //   CHD_EXACT=1      exact bilinear momentum curvature of the dynamics rows + inertia control (negative pivots of the
 //                    band LDL^T must equal the number of equality rows, otherwise delta_w *= CHD_DW_INERTIA (8))
 //   CHD_DW_MIN, CHD_DW_DEC   floor / decay factor of the Levenberg-Marquardt regularisation (1e-8, 3)
+//   CHD_MU_RESCUE=1  lower the barrier floor (x1/5, >= 1e-9) only when every test but the unscaled complementarity passes
 //   CHD_MU_MIN, CHD_MU_SF    barrier floor (default min(tol, compl_inf_tol) / 11; IPOPT's own default is 1e-11)
 //   CHD_NDUR, CHD_DREG       proximal term on the last CHD_NDUR variables (stage-3 duration variables)
 // They document the convergence studies summarised in DESIGN.md section 4.
@@ -367,6 +368,11 @@ struct Solver {
         if (Emu <= o.kappa_eps * mu && mu > mu_min) mu = std::max(mu_min, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
         else break;
       }
+      // experimental (CHD_MU_RESCUE): the scaled error passes but the unscaled complementarity test cannot be met at
+      // the barrier floor (large multipliers make s_c > 11): let the barrier parameter go below the floor, gently
+      if (getenv("CHD_MU_RESCUE") && E0 <= o.tol && violu <= o.constr_viol_tol && dual_u <= o.dual_inf_tol && compl_u > o.compl_inf_tol &&
+          mu <= mu_min * 1.0000001)
+        mu_min = std::max(mu_min / 5.0, 1e-9), mu = mu_min;
       const double tau = std::max(o.tau_min, 1.0 - mu);
       if (it == 0) theta_max = 1e4 * std::max(1.0, theta), theta_min = 1e-4 * std::max(1.0, theta);
       if (mu != mu_filter) filt.clear(), mu_filter = mu;
