@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -45,6 +46,7 @@ int chdo_cost_hessian(void* h, int* ri, int* ci, double* vals);
 int chdo_lag_hessian(void* h, const double* y, int* ri, int* ci, double* vals);
 void chdo_row_times(void* h, double* t);
 void chdo_var_times(void* h, double* t0, double* t1);
+int chdo_dur_blocks(void* h, int* off, int* cnt);
 }
 
 namespace {
@@ -141,10 +143,24 @@ struct Arrow {
   }
 };
 
+// primal-dual state a stage leaves behind, keyed by constraint-set name (the stages stack their sets in different orders)
+struct WarmState {
+  bool valid = false;
+  std::vector<std::string> names;
+  std::vector<int> off, rows;
+  std::vector<double> y, s, zL, zU, sc;
+  double sf = 1.0, mu = 0.1, delta_w = 1e-4;
+};
+
 struct Solver {
+  WarmState* ws = nullptr;   // state of the previous stage of the same problem (nullptr / !valid: cold start)
+  bool warm = false;
   void* h;
   Opts o;
   int n = 0, m = 0;
+  int m0 = 0;                 // rows of the NLP's own constraint sets; rows m0..m-1 are the duration lower bounds d_k >= 0
+  std::vector<int> durk;      // per variable: -1, or k = index of the phase duration inside its PhaseDurations set
+  std::vector<int> dur_vars;  // duration variables in stacking order
   std::vector<double> xlo, xhi, cl, cu;
   std::vector<char> fixed, eq, hasL, hasU, dist_row, dyn_row;
   std::vector<int> vk, rk;  // KKT ordering
@@ -160,8 +176,58 @@ struct Solver {
     chdo_jac(h, ri.data(), ci.data(), jv.data());
     jp.assign(m + 1, 0);
     for (int k = 0; k < nnz; ++k) jp[ri[k] + 1]++;
-    for (int r = 0; r < m; ++r) jp[r + 1] += jp[r];
+    for (int r = 0; r < m0; ++r) jp[r + 1] += jp[r];
     jc = ci;  // triplets are row sorted
+    if (dur_vars.empty()) return;
+    // duration lower bounds as rows, then the change of variables d = D tau (switch times): column tau_k of a row is
+    // (column d_k) - (column d_{k+1}); the dense "all earlier phases" columns of towr's GetJacobianOfPos cancel exactly
+    for (size_t i = 0; i < dur_vars.size(); ++i) jc.push_back(dur_vars[i]), jv.push_back(1.0), jp[m0 + i + 1] = (int)jc.size();
+    std::vector<int> njp(m + 1, 0), njc;
+    std::vector<double> njv, acc(n, 0.0);
+    std::vector<int> touched;
+    std::vector<char> mark(n, 0);
+    for (int r = 0; r < m; ++r) {
+      touched.clear();
+      auto put = [&](int c, double v) {
+        if (!mark[c]) mark[c] = 1, touched.push_back(c);
+        acc[c] += v;
+      };
+      for (int e = jp[r]; e < jp[r + 1]; ++e) {
+        const int c = jc[e];
+        put(c, jv[e]);
+        if (durk[c] > 0) put(c - 1, -jv[e]);
+      }
+      std::sort(touched.begin(), touched.end());
+      for (int c : touched) {
+        if (acc[c] != 0.0) njc.push_back(c), njv.push_back(acc[c]);
+        acc[c] = 0.0, mark[c] = 0;
+      }
+      njp[r + 1] = (int)njc.size();
+    }
+    jp.swap(njp), jc.swap(njc), jv.swap(njv);
+  }
+  void to_tau_grad(std::vector<double>& g) const {   // g_tau_k = g_d_k - g_d_{k+1}
+    for (size_t i = 0; i + 1 < dur_vars.size(); ++i) {
+      const int j = dur_vars[i];
+      if (durk[j + 1] == durk[j] + 1) g[j] -= g[j + 1];
+    }
+  }
+  void to_tau_hess(Triplets& t) const {
+    if (dur_vars.empty()) return;
+    Triplets o;
+    auto img = [&](int v, int (&id)[2], double (&sg)[2]) {
+      id[0] = v, sg[0] = 1.0;
+      if (durk[v] > 0) { id[1] = v - 1, sg[1] = -1.0; return 2; }
+      return 1;
+    };
+    for (size_t k = 0; k < t.v.size(); ++k) {
+      int ir[2], ic[2];
+      double sr[2], scv[2];
+      const int nr = img(t.r[k], ir, sr), nc = img(t.c[k], ic, scv);
+      for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < nc; ++b) o.r.push_back(ir[a]), o.c.push_back(ic[b]), o.v.push_back(sr[a] * scv[b] * t.v[k]);
+    }
+    t = o;
   }
   Triplets hess(bool cost, const double* y) {
     Triplets t;
@@ -169,6 +235,7 @@ struct Solver {
     t.r.resize(nnz), t.c.resize(nnz), t.v.resize(nnz);
     if (cost) chdo_cost_hessian(h, t.r.data(), t.c.data(), t.v.data());
     else chdo_lag_hessian(h, y, t.r.data(), t.c.data(), t.v.data());
+    to_tau_hess(t);
     return t;
   }
 
@@ -224,7 +291,16 @@ struct Solver {
 
   int run(int stage, int max_iter, double* stats, int verbose) {
     chdo_set_stage(h, stage);
-    n = chdo_n(h), m = chdo_m(h);
+    n = chdo_n(h), m0 = chdo_m(h);
+    durk.assign(n, -1);
+    dur_vars.clear();
+    {
+      int off[8], cnt[8];
+      const int nblk = chdo_dur_blocks(h, off, cnt);
+      for (int b = 0; b < nblk; ++b)
+        for (int k = 0; k < cnt[b]; ++k) durk[off[b] + k] = k, dur_vars.push_back(off[b] + k);
+    }
+    m = m0 + (int)dur_vars.size();
     std::vector<double> x(n);
     chdo_get_x(h, x.data());
     xlo.assign(n, 0), xhi.assign(n, 0);
@@ -234,6 +310,7 @@ struct Solver {
       if (xlo[i] == xhi[i]) fixed[i] = 1, x[i] = xlo[i];
     cl.assign(m, 0), cu.assign(m, 0);
     chdo_con_bounds(h, cl.data(), cu.data());
+    for (int r = m0; r < m; ++r) cl[r] = 0.0, cu[r] = 1e20;   // PhaseDurations bounds (0, 500) of parameters.cpp:60: the upper one is implied by the TotalTime rows
     eq.assign(m, 0), hasL.assign(m, 0), hasU.assign(m, 0), dist_row.assign(m, 0), dyn_row.assign(m, 0);
     for (int r = 0; r < m; ++r) {
       eq[r] = cl[r] == cu[r];
@@ -258,24 +335,45 @@ struct Solver {
       f = chdo_cost(h);
       c.resize(m);
       chdo_cons(h, c.data());
+      for (size_t i = 0; i < dur_vars.size(); ++i) c[m0 + i] = xx[dur_vars[i]];
     };
     double f;
     std::vector<double> c, g(n);
     evaluate(x, f, c);
     chdo_grad(h, g.data());
+    to_tau_grad(g);
     eval_jac();
     // gradient based scaling
     double gmax = 0;
     for (int i = 0; i < n; ++i)
       if (!fixed[i]) gmax = std::max(gmax, std::fabs(g[i]));
-    const double sf = gmax > o.scal_max_grad ? o.scal_max_grad / gmax : 1.0;
+    const bool use_warm = warm && ws && ws->valid;
+    const double sf = use_warm ? ws->sf : (gmax > o.scal_max_grad ? o.scal_max_grad / gmax : 1.0);
     std::vector<double> sc(m, 1.0), dL(m), dU(m), s(m), y(m, 0.0), zL(m, 0.0), zU(m, 0.0);
+    // warm start: rows of constraint sets the previous stage also had inherit scaling, slack and multipliers
+    std::vector<int> wsrc(m, -1);
+    std::vector<std::string> set_names;
+    std::vector<int> set_off, set_rows;
+    {
+      int off = 0;
+      for (int i = 0; i < chdo_num_constraint_sets(h); ++i) {
+        set_names.push_back(chdo_constraint_set_name(h, i));
+        set_off.push_back(off), set_rows.push_back(chdo_constraint_set_rows(h, i));
+        if (use_warm)
+          for (size_t q = 0; q < ws->names.size(); ++q)
+            if (ws->names[q] == set_names.back() && ws->rows[q] == set_rows.back())
+              for (int r = 0; r < set_rows.back(); ++r) wsrc[off + r] = ws->off[q] + r;
+        off += set_rows.back();
+      }
+    }
+    const double mu_start = use_warm ? std::max(ws->mu, getenv("CHD_WARM_MU") ? atof(getenv("CHD_WARM_MU")) : 0.0) : o.mu_init;
     int n_bounds = 0;
     for (int r = 0; r < m; ++r) {
       double rm = 0;
       for (int e = jp[r]; e < jp[r + 1]; ++e)
         if (!fixed[jc[e]]) rm = std::max(rm, std::fabs(jv[e]));
       sc[r] = std::max(rm > o.scal_max_grad ? o.scal_max_grad / rm : 1.0, 1e-8);
+      if (wsrc[r] >= 0) sc[r] = ws->sc[wsrc[r]];
       const double lo = cl[r] * sc[r], hi = cu[r] * sc[r], d = sc[r] * c[r];
       if (eq[r]) {
         dL[r] = lo, dU[r] = hi, s[r] = d;
@@ -297,9 +395,20 @@ struct Solver {
       s[r] = sv;
       zL[r] = hasL[r] ? 1.0 : 0.0;
       zU[r] = hasU[r] ? 1.0 : 0.0;
+      if (use_warm) {   // new rows of a warm-started stage start on the central path of the inherited barrier parameter
+        if (hasL[r]) zL[r] = mu_start / (sv - dL[r]);
+        if (hasU[r]) zU[r] = mu_start / (dU[r] - sv);
+      }
       n_bounds += hasL[r] + hasU[r];
     }
-    double mu = o.mu_init, delta_w = o.delta_w0, mu_filter = -1.0, theta_max = 0, theta_min = 0;
+    if (use_warm)
+      for (int r = 0; r < m; ++r) {
+        const int q = wsrc[r];
+        if (q < 0) continue;
+        y[r] = ws->y[q];
+        if (!eq[r]) s[r] = ws->s[q], zL[r] = ws->zL[q], zU[r] = ws->zU[q];
+      }
+    double mu = mu_start, delta_w = use_warm ? std::max(ws->delta_w, o.delta_w0) : o.delta_w0, mu_filter = -1.0, theta_max = 0, theta_min = 0;
     double mu_min = getenv("CHD_MU_MIN") ? atof(getenv("CHD_MU_MIN")) : std::min(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
     if (getenv("CHD_MU_SF")) mu_min = std::min(o.tol, o.compl_inf_tol * sf) / (o.kappa_eps + 1.0);   // the unscaled complementarity test must be reachable
     if (verbose) printf("sf %.4f mu_min %.3e\n", sf, mu_min);
@@ -314,6 +423,12 @@ struct Solver {
     for (int r = 0; r < m; ++r) n_eq_rows += eq[r] && rk[r] >= 0 && rk[r] < Na;
     if (getenv("CHD_DW_MIN")) o.dw_min = atof(getenv("CHD_DW_MIN"));
     if (getenv("CHD_DW_DEC")) o.dw_dec = atof(getenv("CHD_DW_DEC"));
+    const double nl_ke = dur_vars.empty() ? 0.0 : (getenv("CHD_NL_KE") ? atof(getenv("CHD_NL_KE")) : 1.0);   // stage 3 only (CHD_NL_GUARD in chd_dev.h)
+    const double nl_fl = getenv("CHD_NL_FL") ? atof(getenv("CHD_NL_FL")) : 1e-4;
+    double theta_ref = 0.0;
+    const double rt0 = getenv("CHD_RT0") ? atof(getenv("CHD_RT0")) : 0.0, rt_dec = getenv("CHD_RT_DEC") ? atof(getenv("CHD_RT_DEC")) : 3.0;
+    const double rt_min = getenv("CHD_RT_MIN") ? atof(getenv("CHD_RT_MIN")) : 0.0;
+    double rho_tau = dur_vars.empty() ? 0.0 : rt0;
     const int exp_ndur = getenv("CHD_NDUR") ? atoi(getenv("CHD_NDUR")) : 0;
     const double exp_dreg = getenv("CHD_DREG") ? atof(getenv("CHD_DREG")) : 0.0;
     for (it = 0;; ++it) {
@@ -348,11 +463,14 @@ struct Solver {
       auto compl_err = [&](double mm) { return n_bounds > 0 ? std::max(std::fabs(cmax - mm), std::fabs(cmin - mm)) : 0.0; };
       E0 = std::max(std::max(dual_inf / s_d, cviol), compl_err(0.0) / s_c);
       dual_u = dual_inf / sf, compl_u = compl_err(0.0) / sf;
-      if (verbose) printf("it %3d f %.6e E0 %.2e viol %.2e dual %.2e mu %.1e dw %.1e\n", it, f, E0, violu, dual_inf, mu, delta_w);
+      if (verbose) printf("it %3d f %.6e E0 %.2e viol %.2e dual %.2e mu %.1e dw %.1e rt %.1e\n", it, f, E0, violu, dual_inf, mu, delta_w, rho_tau);
       if (verbose > 2) {
         int im = 0; double nrm = 0; int cnt = 0;
         for (int i = 0; i < n; ++i) if (!fixed[i]) { if (std::fabs(rx[i]) > std::fabs(rx[im]) || fixed[im]) im = i; nrm += rx[i] * rx[i]; cnt += std::fabs(rx[i]) > 0.1 * dual_inf; }
         double ymax = 0; int iy = 0; for (int r = 0; r < m; ++r) if (std::fabs(y[r]) > ymax) ymax = std::fabs(y[r]), iy = r;
+{ int iv = 0; double vm = -1; for (int r = 0; r < m; ++r) { double v = std::max(cl[r] - c[r], c[r] - cu[r]); if (v > vm) vm = v, iv = r; }
+          int off = 0; std::string nm = "durpos"; for (int q = 0; q < chdo_num_constraint_sets(h); ++q) { int rows = chdo_constraint_set_rows(h, q); if (iv >= off && iv < off + rows) { nm = chdo_constraint_set_name(h, q); nm += "[" + std::to_string(iv - off) + "/" + std::to_string(rows) + "]"; } off += rows; }
+          printf("      max viol row %d %s (%.3e) sc %.3e s-d %.3e y %.3e\n", iv, nm.c_str(), vm, sc[iv], s[iv] - sc[iv] * c[iv], y[iv]); }
         printf("      argmax rx %d (%.3e) l2 %.3e count>10%% %d | ymax %.3e at row %d | s_d %.3e\n", im, rx[im], std::sqrt(nrm), cnt, ymax, iy, s_d);
       }
       if (E0 <= o.tol && violu <= o.constr_viol_tol && dual_u <= o.dual_inf_tol && compl_u <= o.compl_inf_tol) {
@@ -374,7 +492,7 @@ struct Solver {
           mu <= mu_min * 1.0000001)
         mu_min = std::max(mu_min / 5.0, 1e-9), mu = mu_min;
       const double tau = std::max(o.tau_min, 1.0 - mu);
-      if (it == 0) theta_max = 1e4 * std::max(1.0, theta), theta_min = 1e-4 * std::max(1.0, theta);
+      if (it == 0) theta_max = 1e4 * std::max(1.0, theta), theta_min = 1e-4 * std::max(1.0, theta), theta_ref = theta;
       if (mu != mu_filter) filt.clear(), mu_filter = mu;
       // ---- condensed KKT ----
       for (int r = 0; r < m; ++r) ypos[r] = (dist_row[r] && sc[r] * y[r] > 1e-8) ? sc[r] * y[r] : 0.0;  // CHD_CURV_MIN
@@ -385,7 +503,7 @@ struct Solver {
       w = bandwidth(W1, W2);
       K.init(Na, nb, w);
       for (int i = 0; i < n; ++i)
-        if (vk[i] >= 0) K.add(vk[i], vk[i], delta_w + (i >= n - exp_ndur ? exp_dreg : 0.0)), K.rhs[vk[i]] += -sf * g[i];
+        if (vk[i] >= 0) K.add(vk[i], vk[i], delta_w + (i >= n - exp_ndur ? exp_dreg : 0.0) + (durk[i] >= 0 ? rho_tau : 0.0)), K.rhs[vk[i]] += -sf * g[i];
       for (size_t k = 0; k < W1.v.size(); ++k) {
         int a = vk[W1.r[k]], b = vk[W1.c[k]];
         if (a >= 0 && b >= 0 && a >= b) K.add(a, b, sf * W1.v[k]);
@@ -441,7 +559,7 @@ struct Solver {
         continue;
       }
       // ---- step recovery ----
-      for (int i = 0; i < n; ++i) dx[i] = vk[i] >= 0 ? sol[vk[i]] : 0.0;
+      for (int i = 0; i < n; ++i) dx[i] = vk[i] >= 0 ? sol[vk[i]] : 0.0;   // step in (nodes, switch times)
       double a_pr = 1.0, a_du = 1.0, dphi = 0, phib = 0;
       for (int i = 0; i < n; ++i) dphi += sf * g[i] * dx[i];
       for (int r = 0; r < m; ++r) {
@@ -467,11 +585,15 @@ struct Solver {
         if (hasU[r]) dphi += mu * dsr / gapU, phib -= mu * std::log(gapU);
       }
       const double phi0 = sf * f + phib;
+      for (int i = (int)dur_vars.size() - 1; i >= 0; --i) {   // back to phase durations: dd_k = dtau_k - dtau_{k-1}
+        const int j = dur_vars[i];
+        if (durk[j] > 0) dx[j] -= dx[j - 1];
+      }
       // ---- filter line search ----
       double alpha = a_pr, ft = f;
       if (verbose > 1) printf("      a_pr %.3e a_du %.3e dphi %.3e\n", a_pr, a_du, dphi);
       bool accepted = false, ftype = false;
-      int ls = 0;
+      int ls = 0, nl_rej = 0;
       for (ls = 0; ls < o.max_backtrack; ++ls) {
         for (int i = 0; i < n; ++i) xt[i] = x[i] + alpha * dx[i];
         evaluate(xt, ft, ct);
@@ -488,6 +610,9 @@ struct Solver {
         }
         const double phit = sf * ft + bar;
         bool okp = std::isfinite(phit) && std::isfinite(theta_t) && theta_t <= theta_max;
+        // nonlinearity guard: the linearised constraints predict theta(alpha) = (1 - alpha) theta; the trial point is
+        // refused while the second-order error exceeds nl_ke x the predicted decrease (or a small absolute level)
+        if (nl_ke > 0.0 && okp && theta_t - (1.0 - alpha) * theta > nl_ke * std::max(alpha * theta, nl_fl * std::max(1.0, theta_ref))) okp = false, nl_rej++;
         for (auto& e : filt)
           if (okp && theta_t >= e.first && phit >= e.second) okp = false;
         if (okp) {
@@ -509,8 +634,18 @@ struct Solver {
         ls_fail++;
       }
       if (accepted && !ftype && (int)filt.size() < o.filt_max) filt.emplace_back((1 - o.gamma_theta) * theta, phi0 - o.gamma_phi * theta);
-      if (ls == 0) delta_w = std::max(delta_w / o.dw_dec, o.dw_min);
-      else delta_w = std::min(delta_w * std::pow(o.dw_inc, (double)std::min(ls, 3)), o.dw_max);
+      {
+        const int ls_f = rt0 > 0.0 ? ls - nl_rej : ls;   // trials refused by the filter itself
+        const double dec3 = (!dur_vars.empty() && getenv("CHD_DW_DEC3")) ? atof(getenv("CHD_DW_DEC3")) : o.dw_dec;
+        const double inc3 = (!dur_vars.empty() && getenv("CHD_DW_INC3")) ? atof(getenv("CHD_DW_INC3")) : o.dw_inc;
+        const int cap3 = (!dur_vars.empty() && getenv("CHD_LS_CAP3")) ? atoi(getenv("CHD_LS_CAP3")) : 3;
+        if (ls_f == 0) delta_w = std::max(delta_w / dec3, o.dw_min);
+        else delta_w = std::min(delta_w * std::pow(inc3, (double)std::min(ls_f, cap3)), o.dw_max);
+        if (rt0 > 0.0) {
+          if (nl_rej == 0) rho_tau = std::max(rho_tau / rt_dec, rt_min);
+          else rho_tau = std::min(std::max(rho_tau, 1e-6) * std::pow(o.dw_inc, (double)std::min(nl_rej, 3)), 1e6);
+        }
+      }
       x = xt;
       for (int r = 0; r < m; ++r) {
         y[r] += alpha * dy[r];
@@ -527,9 +662,16 @@ struct Solver {
       }
       evaluate(x, f, c);
       chdo_grad(h, g.data());
+      to_tau_grad(g);
       eval_jac();
     }
     chdo_set_x(h, x.data());
+    if (ws) {
+      ws->valid = true;
+      ws->names = set_names, ws->off = set_off, ws->rows = set_rows;
+      ws->y = y, ws->s = s, ws->zL = zL, ws->zU = zU, ws->sc = sc;
+      ws->sf = sf, ws->mu = mu, ws->delta_w = delta_w;
+    }
     if (stats) {
       stats[0] = f, stats[1] = E0, stats[2] = violu, stats[3] = dual_u, stats[4] = compl_u, stats[5] = mu, stats[6] = delta_w, stats[7] = ls_fail;
       stats[8] = it, stats[9] = Na, stats[10] = nb, stats[11] = w;
@@ -543,9 +685,14 @@ struct Solver {
 extern "C" {
 // Solves one stage in place (warm start from the problem's current variables).  stats: 12 doubles
 // (f, E0, unscaled violation, unscaled dual inf, unscaled complementarity, mu, delta_w, ls failures, iterations, Na, nb, w).
+static std::map<void*, WarmState> g_warm;
 int chdo_solve_stage(void* h, int stage, int max_iter, double* stats, int verbose) {
   Solver S;
   S.h = h;
+  S.ws = &g_warm[h];
+  // stage 3 (id 4) continues from the primal-dual point of stage 2.2; every other stage starts cold like IPOPT
+  S.warm = stage == 4 && !(getenv("CHD_WARM") && atoi(getenv("CHD_WARM")) == 0);
   return S.run(stage, max_iter, stats, verbose);
 }
+void chdo_forget(void* h) { g_warm.erase(h); }
 }

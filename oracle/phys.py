@@ -63,6 +63,8 @@ def lib():
             ("chdo_cost_hessian", C.c_int, [C.c_void_p, ip, ip, dp]),
             ("chdo_lag_hessian", C.c_int, [C.c_void_p, dp, ip, ip, dp]),
             ("chdo_row_times", None, [C.c_void_p, dp]),
+            ("chdo_forget", None, [C.c_void_p]),
+            ("chdo_dur_blocks", C.c_int, [C.c_void_p, ip, ip]),
             ("chdo_var_times", None, [C.c_void_p, dp, dp]),
             ("chdo_solve_stage", C.c_int, [C.c_void_p, C.c_int, C.c_int, dp, C.c_int]),
             ("chdo_sample", C.c_int, [C.c_void_p, dp]),
@@ -108,6 +110,7 @@ class OracleProblem:
 
     def __del__(self):
         try:
+            self.L.chdo_forget(self.h)
             self.L.chdo_destroy(self.h)
         except Exception:
             pass
@@ -218,19 +221,26 @@ class OracleProblem:
                     nb=int(stats[10]), w=int(stats[11]))
 
     def solve(self):
-        """Staged schedule as the product runs it: 1.1, 1.2 | 2.1, 2.2 | 4 with the three SaveSolution snapshots."""
+        """Staged schedule of phys_optim.cpp:554-749: 1.1, 1.2 | 2.1, 2.2 | 3 (| 4 only if stage 3 failed, :713-749)
+        with the three SaveSolution snapshots.  `stages` lists the solved stages in order; `stage_ids` names them."""
         out = {}
-        res = []
+        res, ids = [], []
         for st in ("1.1", "1.2"):
-            res.append(self.solve_stage(st))
+            res.append(self.solve_stage(st)), ids.append(st)
         out["no_dynamics"] = self.sample()
         for st in ("2.1", "2.2"):
-            res.append(self.solve_stage(st))
+            res.append(self.solve_stage(st)), ids.append(st)
         out["dynamics"] = self.sample()
-        res.append(self.solve_stage("4"))
+        dyn_ok = res[3]["status"] == 0
+        res.append(self.solve_stage("3")), ids.append("3")
+        dur_ok = res[-1]["status"] == 0                      # :709
+        if not dur_ok:
+            res.append(self.solve_stage("4")), ids.append("4")
+            dur_ok = res[-1]["status"] == 0                  # :746
         out["durations"] = self.sample()
         out["stages"] = res
-        out["success"] = (res[3]["status"] == 0, res[4]["status"] == 0)
+        out["stage_ids"] = ids
+        out["success"] = (dyn_ok, dur_ok)
         return out
 
     def sample(self):

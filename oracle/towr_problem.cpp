@@ -1007,6 +1007,19 @@ void chdo_var_bounds(void* h, double* lo, double* hi) {
     for (auto& d : P->dur)
       for (int i = 0; i < d.rows(); ++i) lo[d.offset + i] = d.lo, hi[d.offset + i] = d.hi;
 }
+// duration variable blocks of the current stage (stage 3 only): offsets and sizes of the PhaseDurations sets in x;
+// returns the number of blocks (0 when the durations are not optimised)
+int chdo_dur_blocks(void* h, int* off, int* cnt) {
+  Problem* P = (Problem*)h;
+  if (!P->opt_dur) return 0;
+  int k = 0;
+  for (auto& d : P->dur) {
+    if (off) off[k] = d.offset;
+    if (cnt) cnt[k] = d.rows();
+    ++k;
+  }
+  return k;
+}
 int chdo_num_constraint_sets(void* h) { return (int)((Problem*)h)->cons.size(); }
 int chdo_constraint_set_rows(void* h, int i) { return ((Problem*)h)->cons[i]->rows; }
 const char* chdo_constraint_set_name(void* h, int i) { return ((Problem*)h)->cons[i]->name.c_str(); }
