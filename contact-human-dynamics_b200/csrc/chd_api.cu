@@ -20,6 +20,9 @@ __global__ void chd_k_curv(ChdDev D);
 __global__ void chd_k_asm(ChdDev D);
 __global__ void chd_k_fp64_peak(int mode, int iters, double* sink);
 __global__ void chd_k_hess_base(ChdDev D);
+__global__ void chd_k_hess_dur(ChdDev D);
+__global__ void chd_k_tables(ChdDev D);
+__global__ void chd_k_clear_dyn(ChdDev D);
 __global__ void chd_k_linesearch(ChdDev D);
 __global__ void chd_k_sample(ChdDev D, double* out, int* frames_out);
 __global__ void chd_k_snapshot(ChdDev D, int* frames_out);
@@ -57,6 +60,10 @@ struct chd_phys_batch {
   int64_t h2d_bytes = 0;
   ChdStageDev* d_stages = nullptr;
   int sched_max_iter = 0;
+  bool sched_has_dur = false;   // the running schedule contains stage 3 (its cost Hessian is rebuilt every iteration)
+  // pristine copies of the tables stage 3 rewrites (chd_phys_reset)
+  double *poly_T0 = nullptr, *poly_tend0 = nullptr, *phase_tend0 = nullptr;
+  int* ent_col0 = nullptr;
 };
 
 namespace {
@@ -87,8 +94,9 @@ ChdStageDev stage_dev(const ChdStageCfg& c, int stage) {
   s.set_mask = c.set_mask;
   s.max_iter = c.max_iter;
   s.snap_after = stage == CHD_STAGE_12 ? 0 : (stage == CHD_STAGE_22 ? 1 : ((stage == CHD_STAGE_4 || stage == CHD_STAGE_3) ? 2 : -1));
-  s.pad = 0;
+  s.opt_dur = stage == CHD_STAGE_3;
   for (int i = 0; i < 3; ++i) s.w_data[i] = c.w_data[i], s.w_vel[i] = c.w_vel[i], s.w_acc[i] = c.w_acc[i];
+  s.w_dur = c.w_dur;
   return s;
 }
 
@@ -126,7 +134,8 @@ int set_schedule(chd_phys_batch* b, const int* sched, int nsched, int override_s
   b->D.nsched = nsched;
   for (int i = 0; i < nsched; ++i) b->D.sched[i] = sched[i];
   b->sched_max_iter = 0;
-  for (int i = 0; i < nsched; ++i) b->sched_max_iter += tab[sched[i]].max_iter + 2;
+  b->sched_has_dur = false;
+  for (int i = 0; i < nsched; ++i) b->sched_max_iter += tab[sched[i]].max_iter + 2, b->sched_has_dur |= sched[i] == CHD_STAGE_3;
   chd_k_sched_reset<<<(b->hb.B + 127) / 128, 128, 0, b->stream>>>(b->D);
   b->launches++;
   return 0;
@@ -160,11 +169,14 @@ int run_schedule(chd_phys_batch* b) {
       if (b->D.win_smem) chd_k_kkt<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);
       else chd_k_kkt_gwin<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);
     }
-    // Kwork <- Kbase for the next iteration, overlapped with the line search / evaluation kernels
-    CHD_CUDA(cudaEventRecord(b->ev_kkt, b->stream));
-    CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_kkt, 0));
-    chd_k_kcopy<<<dim3(b->kcopy_blocks, B), 256, 0, b->copy_stream>>>(b->D);
-    b->launches++;
+    // Kwork <- Kbase for the next iteration, overlapped with the line search / evaluation kernels.  With stage 3 in the
+    // schedule the cost Hessian (Kbase) of the sequences in that stage is rebuilt from the accepted iterate first.
+    if (!b->sched_has_dur) {
+      CHD_CUDA(cudaEventRecord(b->ev_kkt, b->stream));
+      CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_kkt, 0));
+      chd_k_kcopy<<<dim3(b->kcopy_blocks, B), 256, 0, b->copy_stream>>>(b->D);
+      b->launches++;
+    }
     {
       Timer t(b, KT_LS);
       chd_k_linesearch<<<B, CHD_THREADS, b->smem_ls, b->stream>>>(b->D);
@@ -172,6 +184,11 @@ int run_schedule(chd_phys_batch* b) {
     // distance-row curvature of the next iteration needs the accepted iterate: after the line search, on the side stream
     CHD_CUDA(cudaEventRecord(b->ev_ls, b->stream));
     CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_ls, 0));
+    if (b->sched_has_dur) {
+      chd_k_hess_dur<<<B, CHD_THREADS, 0, b->copy_stream>>>(b->D);
+      chd_k_kcopy<<<dim3(b->kcopy_blocks, B), 256, 0, b->copy_stream>>>(b->D);
+      b->launches += 2;
+    }
     chd_k_curv<<<dim3(8, B), 256, 0, b->copy_stream>>>(b->D);
     b->launches++;
     CHD_CUDA(cudaEventRecord(b->ev_copy, b->copy_stream));
@@ -273,15 +290,26 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   CHD_CUDA(cudaEventCreate(&b->ev0));
   CHD_CUDA(cudaEventCreate(&b->ev1));
 #define UP(field) if ((rc = dev_upload(b, hb.field, &D.field))) return rc;
-  UP(seq) UP(poly_T) UP(poly_tend) UP(node_const) UP(par) UP(t_dyn) UP(t_rom) UP(t_data) UP(row_lo) UP(row_hi) UP(node_var)
-  UP(itab) UP(ent_ptr) UP(ent_col) UP(ent_row) UP(col_ptr) UP(col_ent) UP(var_kkt) UP(row_kkt) UP(row_set) UP(sets) UP(phase_tend)
+#define UPM(field, T) if ((rc = dev_upload(b, hb.field, (const T**)&D.field))) return rc;
+  UP(seq) UPM(poly_T, double) UPM(poly_tend, double) UP(node_const) UP(par) UP(t_dyn) UP(t_rom) UP(t_data) UP(row_lo) UP(row_hi) UP(node_var)
+  UP(itab) UP(ent_ptr) UPM(ent_col, int) UP(ent_row) UP(col_ptr) UP(col_ent) UP(var_kkt) UP(row_kkt) UP(row_set) UP(sets) UPM(phase_tend, double)
+  UP(dur0) UP(poly_ph)
+  // pristine copies of what stage 3 rewrites + the line search's trial tables
+  if ((rc = dev_upload(b, hb.poly_T, (const double**)&b->poly_T0))) return rc;
+  if ((rc = dev_upload(b, hb.poly_tend, (const double**)&b->poly_tend0))) return rc;
+  if ((rc = dev_upload(b, hb.phase_tend, (const double**)&b->phase_tend0))) return rc;
+  if ((rc = dev_upload(b, hb.ent_col, (const int**)&b->ent_col0))) return rc;
+  if ((rc = dev_upload(b, hb.poly_T, (const double**)&D.poly_Tt))) return rc;
+  if ((rc = dev_upload(b, hb.poly_tend, (const double**)&D.poly_tendt))) return rc;
+#undef UPM
 #undef UP
   const size_t B = hb.B, nm = B * hb.n_max, mm = B * hb.m_max;
 #define AL(field, cnt) if ((rc = dev_alloc(b, (cnt), &D.field))) return rc;
-  AL(x, nm) AL(xt, nm) AL(dx, nm) AL(grad, nm) AL(g, mm) AL(gt, mm) AL(Jv, B * hb.slots_max) AL(rflag, mm)
+  AL(x, nm) AL(xt, nm) AL(jty, nm) AL(dx, nm) AL(grad, nm) AL(g, mm) AL(gt, mm) AL(Jv, B * hb.slots_max) AL(rflag, mm)
   AL(sc, mm) AL(dL, mm) AL(dU, mm) AL(s, mm) AL(y, mm) AL(zL, mm) AL(zU, mm) AL(ds, mm) AL(dy, mm) AL(dzL, mm) AL(dzU, mm)
   D.nbc_max = (hb.Na_max + 7) / 8;
   D.Q = (hb.w_max + 7) / 8 + 1;
+  D.Qfix = (hb.w_fix_max + 7) / 8 + 1;   // band tiles the fixed-duration stages work with (storage strides follow Q)
   D.nbt = (hb.nb_max + 1 + 7) / 8;
   D.win_tiles = std::max(D.Q * (D.Q + 1) / 2, 2 * D.Q);
   D.kstride = (size_t)D.nbc_max * D.Q * 64 + (size_t)D.nbc_max * D.nbt * 64 + (size_t)64 * D.nbt * D.nbt;
@@ -300,12 +328,14 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   CHD_CUDA(cudaFuncGetAttributes(&fa, chd_k_kkt));
   const size_t kkt_static = fa.sharedSizeBytes;
   const size_t n_even = (size_t)((hb.n_max + 1) & ~1), xs_len = 8 * (size_t)D.nbc_max + nbp8;
-  const size_t kkt_fixed = (CHD_KKT_THREADS + n_even + xs_len + nbp8 * nbp8 + (size_t)D.pan_doubles + 16) * sizeof(double);
+  // the per-unknown vectors alias the tail of the window region (chd_kkt_body)
+  const size_t kkt_fixed = (CHD_KKT_THREADS + nbp8 * nbp8 + (size_t)D.pan_doubles + 16) * sizeof(double);
   const size_t kkt_win = ((size_t)D.win_tiles * 64 + (size_t)D.Q * D.nbt * 64) * sizeof(double);
   int dev = 0, smem_max = 0;
   CHD_CUDA(cudaGetDevice(&dev));
   CHD_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (kkt_fixed + kkt_win + kkt_static + 256 <= (size_t)smem_max) {
+  const bool vectors_fit = (size_t)D.win_tiles * 64 + (size_t)D.Q * D.nbt * 64 >= n_even + xs_len + 2 * (size_t)D.Q * 64 + 3072;
+  if (vectors_fit && kkt_fixed + kkt_win + kkt_static + 256 <= (size_t)smem_max) {
     D.win_smem = 1;
     b->smem_kkt = kkt_fixed + kkt_win;
   } else {
@@ -313,7 +343,7 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
     D.win_smem = 0;
     D.pan_doubles = 2 * (D.Q + D.nbt) * 64;
     b->smem_kkt = (CHD_KKT_THREADS + nbp8 * nbp8 + (size_t)D.pan_doubles + 16) * sizeof(double);
-    D.scratch_stride = n_even + xs_len + 8 * (size_t)D.nbc_max + kkt_win / sizeof(double);
+    D.scratch_stride = n_even + xs_len + 8 * (size_t)D.nbc_max + (size_t)D.win_tiles * 64 + (size_t)D.Q * D.nbt * 64;
     if ((rc = dev_alloc(b, B * D.scratch_stride, &D.scratch))) return rc;
     if (D.Q - 1 + D.nbt > 76) {
       fprintf(stderr, "libchd: band + border too wide for the pair tables (Q=%d nbt=%d)\n", D.Q, D.nbt);
@@ -389,6 +419,9 @@ int chd_phys_get_x(const chd_phys_batch* b, double* x) {
 int chd_phys_set_x(chd_phys_batch* b, const double* x) {
   if (!b || !x || b->host_only) return -1;
   CHD_CUDA(cudaMemcpy(b->D.x, x, (size_t)b->hb.B * b->hb.n_max * sizeof(double), cudaMemcpyHostToDevice));
+  chd_k_tables<<<b->hb.B, 64, 0, b->stream>>>(b->D);   // spline tables follow the durations held in x
+  b->launches++;
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
   return 0;
 }
 
@@ -440,6 +473,43 @@ int chd_phys_get_slot_index(const chd_phys_batch* b, int32_t* ent_row, int32_t* 
   return 0;
 }
 
+int chd_phys_get_ent_col(const chd_phys_batch* b, int32_t* ent_col) {
+  if (!b || !ent_col) return -1;
+  if (b->host_only) {
+    std::memcpy(ent_col, b->hb.ent_col.data(), b->hb.ent_col.size() * sizeof(int));
+    return 0;
+  }
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
+  CHD_CUDA(cudaMemcpy(ent_col, b->D.ent_col, b->hb.ent_col.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int chd_phys_get_duals(const chd_phys_batch* b, double* y, double* zL, double* zU, double* s, double* row_scale, double* obj_scale) {
+  if (!b || b->host_only) return -1;
+  const size_t B = b->hb.B, mm = B * b->hb.m_max;
+  CHD_CUDA(cudaStreamSynchronize(b->stream));
+  if (y) CHD_CUDA(cudaMemcpy(y, b->D.y, mm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (zL) CHD_CUDA(cudaMemcpy(zL, b->D.zL, mm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (zU) CHD_CUDA(cudaMemcpy(zU, b->D.zU, mm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (s) CHD_CUDA(cudaMemcpy(s, b->D.s, mm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (row_scale) CHD_CUDA(cudaMemcpy(row_scale, b->D.sc, mm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (obj_scale) {
+    std::vector<ChdIpm> ipm(B);
+    CHD_CUDA(cudaMemcpy(ipm.data(), b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < B; ++i) obj_scale[i] = ipm[i].sf;
+  }
+  return 0;
+}
+
+int chd_phys_stage_stats(const chd_phys_batch* b, double* stats) {
+  if (!b || !stats || b->host_only || !b->h_ipm) return -1;
+  const int B = b->hb.B;
+  for (int s = 0; s < 6; ++s)
+    for (int i = 0; i < B; ++i)
+      for (int q = 0; q < 4; ++q) stats[((size_t)s * B + i) * 4 + q] = b->h_ipm[i].st_stat[s][q];
+  return 0;
+}
+
 int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int32_t* status, int32_t* iters, double* stats) {
   if (!b || stage < 0 || stage > 5 || b->host_only) return -1;
   const int B = b->hb.B;
@@ -480,24 +550,25 @@ int chd_phys_sample(chd_phys_batch* b, double* out, int32_t* frames_out) {
   return 0;
 }
 
-// Staged schedule of phys_optim.cpp:554-749.  Every sequence walks through 1.1, 1.2, 2.1, 2.2, 4 at its own pace
-// (converged sequences do not wait for the slowest one of their stage).  Stage 3 (phase-duration optimisation)
-// is not yet implemented on the device: like the reference when its stage 3 fails (phys_optim.cpp:713-749) the
-// schedule continues with the fixed-duration stage 4 and reports durations_succeed from it.
+// Staged schedule of phys_optim.cpp:554-749.  Every sequence walks through 1.1, 1.2, 2.1, 2.2, 3 and -- only when its
+// stage 3 did not succeed (:713-749) -- 4 at its own pace (converged sequences do not wait for the slowest one of
+// their stage).  Stage status -9 = stage not run (stage 4 after a successful stage 3), -3 = stage 3 not attempted
+// (more phase durations than CHD_MAX_DUR).
 int chd_phys_solve(chd_phys_batch* b, double* samples, int32_t* frames_out, int32_t* success, int32_t* stage_status,
                    int32_t* stage_iters) {
   if (!b || b->host_only) return -1;
   const ChdHostBatch& hb = b->hb;
   const int B = hb.B;
   const size_t stride = 6 + 7 * (size_t)hb.n_ee_max, snap = (size_t)B * hb.fo_max * stride;
-  int sched[5] = {CHD_STAGE_11, CHD_STAGE_12, CHD_STAGE_21, CHD_STAGE_22, CHD_STAGE_4};
-  int rc = set_schedule(b, sched, 5, -1, 0);
+  int sched[6] = {CHD_STAGE_11, CHD_STAGE_12, CHD_STAGE_21, CHD_STAGE_22, CHD_STAGE_3, CHD_STAGE_4};
+  int rc = set_schedule(b, sched, 6, -1, 0);
   if (rc) return rc;
   if (samples) CHD_CUDA(cudaMemsetAsync(b->D.snapshots, 0, 3 * snap * sizeof(double), b->stream));
   if ((rc = run_schedule(b))) return rc;
   for (int i = 0; i < B; ++i) {
     const ChdIpm& I = b->h_ipm[i];
-    if (success) success[2 * i] = I.st_status[CHD_STAGE_22] == 0, success[2 * i + 1] = I.st_status[CHD_STAGE_4] == 0;  // :655, :746
+    // dynamics_succeed (:655); durations_succeed = stage 3 (:709), overwritten by stage 4 when that had to run (:746)
+    if (success) success[2 * i] = I.st_status[CHD_STAGE_22] == 0, success[2 * i + 1] = I.st_status[CHD_STAGE_3] == 0 || I.st_status[CHD_STAGE_4] == 0;
     for (int s = 0; s < 6; ++s) {
       if (stage_status) stage_status[(size_t)s * B + i] = I.st_status[s];
       if (stage_iters) stage_iters[(size_t)s * B + i] = I.st_iters[s];
@@ -514,6 +585,14 @@ int64_t chd_phys_h2d_bytes(const chd_phys_batch* b) { return b ? b->h2d_bytes : 
 int chd_phys_reset(chd_phys_batch* b) {
   if (!b || b->host_only) return -1;
   CHD_CUDA(cudaMemcpyAsync(b->D.x, b->d_x0, (size_t)b->hb.B * b->hb.n_max * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  // the input durations are back: host-built spline tables and Jacobian columns
+  const ChdHostBatch& hb = b->hb;
+  CHD_CUDA(cudaMemcpyAsync(b->D.poly_T, b->poly_T0, hb.poly_T.size() * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  CHD_CUDA(cudaMemcpyAsync(b->D.poly_tend, b->poly_tend0, hb.poly_tend.size() * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  CHD_CUDA(cudaMemcpyAsync(b->D.phase_tend, b->phase_tend0, hb.phase_tend.size() * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  CHD_CUDA(cudaMemcpyAsync(b->D.ent_col, b->ent_col0, hb.ent_col.size() * sizeof(int), cudaMemcpyDeviceToDevice, b->stream));
+  chd_k_clear_dyn<<<(hb.B + 127) / 128, 128, 0, b->stream>>>(b->D);
+  b->launches++;
   return 0;
 }
 int chd_phys_set_timing(chd_phys_batch* b, int enable) {

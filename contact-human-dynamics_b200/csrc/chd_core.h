@@ -28,7 +28,12 @@ enum ChdSetType : int {
   CHD_SET_FORCE = 4,    // towr ForceConstraint     (nlp_formulation.cpp:334-346); a = ee
   CHD_SET_HEEL = 5,     // ee_dist_constraint.cpp;                                 a,b = ee pair
   CHD_SET_HEIGHT = 6,   // height_constraint.cpp;                                  a = ee
+  CHD_SET_TOTTIME = 7,  // total_duration_constraint.cpp:60-82 (stage 3 only);     a = ee, one row
+  CHD_SET_DURPOS = 8,   // PhaseDurations bounds (0, 500) of parameters.cpp:60 as rows d_k >= 0 (stage 3 only); a = ee
 };
+#define CHD_TAU_TRUST 0.04   /* [s] stage 3 keeps every switch time within this distance of its input value: the layout sizes the
+                                band for the polynomials that can move onto a sample time within it (line-search trials beyond are refused) */
+#define CHD_MAX_DUR 96   /* most phase-duration variables (sum over feet of P-1) stage 3 handles as dense border unknowns */
 // stage bit masks over set types (phys_optim.cpp:554-749)
 #define CHD_MASK(t) (1u << (t))
 enum ChdStage : int { CHD_STAGE_11 = 0, CHD_STAGE_12 = 1, CHD_STAGE_21 = 2, CHD_STAGE_22 = 3, CHD_STAGE_3 = 4, CHD_STAGE_4 = 5 };
@@ -46,10 +51,13 @@ CHD_HD int chd_slots_per_row(int type, int n_ee) {
     case CHD_SET_ACC: return 6;
     case CHD_SET_TERRAIN: return 3;
     case CHD_SET_FORCE: return 3;
-    case CHD_SET_ROM: return 36;
-    case CHD_SET_DYN: return 24 + 24 * n_ee;
-    case CHD_SET_HEEL: return 24;
-    default: return 12;  // HEIGHT
+    // time-located rows end with two switch-time slots per foot they touch (stage 3; columns -1 otherwise)
+    case CHD_SET_ROM: return 36 + 2;
+    case CHD_SET_DYN: return 24 + 24 * n_ee + 2 * n_ee;
+    case CHD_SET_HEEL: return 24 + 4;
+    case CHD_SET_TOTTIME: return 1;
+    case CHD_SET_DURPOS: return 2;
+    default: return 12 + 2;  // HEIGHT
   }
 }
 
@@ -61,7 +69,12 @@ struct ChdSeq {
   int nsets;
   int nslots;     // Jacobian value slots
   int n_dyn, n_rom, n_smooth;
-  int Na, nb, w;  // KKT: banded unknowns, border unknowns, half bandwidth
+  int Na, nb, w;  // KKT: banded unknowns, border unknowns (stance positions, then the switch times), half bandwidth
+  int n_dur;      // phase-duration variables (0: stage 3 not available for this sequence), the last n_dur entries of x
+  int nb_fix;     // border unknowns of the fixed-duration stages (= nb - n_dur)
+  int w_fix;      // half bandwidth of the fixed-duration stages (static pattern); w additionally covers the polynomials
+                  // stage 3 may move onto a sample time
+  int dur_xoff[CHD_MAX_EE];   // first duration variable of every foot (P - 1 of them)
   double dt, T, mass, grav, mu, max_leg, max_heel, heel_dist, force_limit;
   double normal[3], point[3], gvec[3], nrm[3], tan1[3], tan2[3], dhdx, dhdy;
   int sp_npoly[CHD_MAX_SPLINES];

@@ -6,6 +6,8 @@
 #define CHD_FILT_MAX 24
 #define CHD_THREADS 512
 #define CHD_KKT_THREADS 512
+#define CHD_NL_GUARD 1.0    /* stage 3 line search: trial refused while theta_t - (1-alpha) theta > CHD_NL_GUARD * max(alpha theta, CHD_NL_FLOOR max(1, theta_ref)) */
+#define CHD_NL_FLOOR 1e-4
 #define CHD_CURV_MIN 1e-8   /* multiplier threshold below which y^+ Jd^T Jd is not added (same in oracle/ipm_oracle.cpp) */
 
 // row flags
@@ -13,6 +15,7 @@
 #define CHD_ROW_EQ 2
 #define CHD_ROW_HASL 4
 #define CHD_ROW_HASU 8
+#define CHD_ROW_WARM 16   /* row keeps the interior-point state of the previous stage (stage 3 after 2.2) */
 
 // Interior-point state of one sequence ("chd-ipm").
 #define CHD_PH_BEGIN 0
@@ -23,12 +26,19 @@ struct ChdIpm {
   int iter, nfilt, ls_fail, max_iter, n_bounds, m_act, pad0;
   // schedule state: every sequence walks through the staged schedule at its own pace
   int stage, pos, phase, snap, step_ready;
+  int last_p1;  // 1 + id of the stage this sequence completed last (0: none since the last reset); stage 3 starts from the
+                // primal-dual point of stage 2.2 when that is what ran before it
+  int warm;     // this stage was warm started
+  int dyn;      // the durations have left their input values (stage 3 ran): spline tables and Jacobian columns are run-time data
+  int band_ovf; // a coupling fell outside the band sized by the layout (stage 3 moved a polynomial too far): the stage fails
   int kw_req;   // the KKT kernel asks for Kwork <- Kbase to be refreshed by the side-stream copy before its next launch
   int st_status[6], st_iters[6];
   double mu, delta_w, sf, theta_max, theta_min, mu_filter, tau;
   double f, E0, viol_u, dual_u, compl_u;          // error measures at the current iterate
   double phi0, theta0, dphi, a_pr, a_du;          // line-search inputs produced by the KKT kernel
+  double theta_ref;                               // theta at the first iteration of the stage (nonlinearity guard of stage 3)
   double filt[2 * CHD_FILT_MAX];
+  double st_stat[6][4];                           // per stage at its end: f, E0 (scaled NLP error), unscaled constraint violation, unscaled dual infeasibility
   double prof[8];   // clock64 cycles per phase of chd_k_kkt (0 errors, 1 J assembly, 2 Hessian assembly, 3 factor, 4 border, 5 back-subst, 6 step recovery)
 };
 
@@ -36,21 +46,26 @@ struct ChdStageDev {
   unsigned set_mask;
   int max_iter;
   int snap_after;   // SaveSolution snapshot written when the stage ends (-1: none)
-  int pad;
-  double w_data[3], w_vel[3], w_acc[3];
+  int opt_dur;      // stage 3: the phase durations are unknowns (as switch times), warm start from the previous stage
+  double w_data[3], w_vel[3], w_acc[3], w_dur;
 };
 
 struct ChdDev {
   int B, S, Pmax, n_max, m_max, slots_max, sets_max, tab_max, F_max, Kd_max, Kr_max, Na_max, nb_max, w_max, par_stride,
-      n_ee_max, fo_max, Ph_max, win_smem, nbc_max, Q, nbt, win_tiles, pan_doubles;
+      n_ee_max, fo_max, Ph_max, win_smem, nbc_max, Q, Qfix, nbt, win_tiles, pan_doubles;
   size_t kstride;                             // doubles per sequence of a tile-format KKT buffer (band | bord | corn)
   // ---- static layout ----
   const ChdSeq* seq;
-  const double *poly_T, *poly_tend, *node_const, *par, *t_dyn, *t_rom, *t_data, *row_lo, *row_hi;
-  const int *node_var, *itab, *ent_ptr, *ent_col, *var_kkt, *row_kkt, *row_set;
+  // poly_T / poly_tend / phase_tend / ent_col are rewritten on the device once stage 3 moves the durations
+  double *poly_T, *poly_tend;
+  const double *node_const, *par, *t_dyn, *t_rom, *t_data, *row_lo, *row_hi, *dur0;
+  const int *node_var, *itab, *ent_ptr, *var_kkt, *row_kkt, *row_set, *poly_ph;
+  int* ent_col;
+  double *poly_Tt, *poly_tendt;                // tables of the line search's trial durations (stage 3)
+  double* jty;                                // B x n_max  J^T y accumulator of sequences with run-time columns
   const int *ent_row, *col_ptr, *col_ent;      // row of every slot; slots by column
   const ChdSet* sets;
-  const double* phase_tend;                   // B x n_ee_max x Ph_max cumulative phase end times
+  double* phase_tend;                         // B x n_ee_max x Ph_max cumulative phase end times
   // ---- iterate ----
   double *x, *xt, *dx, *grad;                 // B x n_max
   double *g, *gt;                             // B x m_max   (unscaled constraint values at x / trial x)
@@ -100,3 +115,22 @@ struct ChdDev {
 #define CHD_S_THETA 1.1
 #define CHD_ETA_PHI 1e-8
 #define CHD_INF 1e19
+
+#if defined(__CUDACC__) || defined(CHD_HOST_EMU)
+// a stage ended for this sequence: record its outcome, request the snapshot, move on in the schedule
+// (phys_optim.cpp:709-749: stage 4 only runs when stage 3 did not succeed)
+__device__ __forceinline__ void chd_stage_advance(const ChdDev& D, ChdIpm& I, int status, int snap_after) {
+  I.st_status[I.stage] = status;
+  I.st_iters[I.stage] = I.iter;
+  I.st_stat[I.stage][0] = I.f, I.st_stat[I.stage][1] = I.E0, I.st_stat[I.stage][2] = I.viol_u, I.st_stat[I.stage][3] = I.dual_u;
+  I.last_p1 = I.stage + 1;
+  I.step_ready = 0;
+  I.kw_req = 0;
+  I.pos += 1;
+  if (I.stage == CHD_STAGE_3 && status == 0 && I.pos < D.nsched && D.sched[I.pos] == CHD_STAGE_4) I.pos += 1;
+  else if (I.stage == CHD_STAGE_3 && status != 0 && I.pos < D.nsched && D.sched[I.pos] == CHD_STAGE_4) snap_after = -1;  // SaveSolution comes after stage 4 (:758)
+  I.snap = snap_after;
+  if (I.pos < D.nsched) I.stage = D.sched[I.pos], I.phase = CHD_PH_BEGIN;
+  else I.phase = CHD_PH_FINISHED;
+}
+#endif

@@ -11,10 +11,13 @@
 struct ChdCtx {
   const ChdSeq* h;
   const double* x;           // current point (shared or global memory)
-  const double *poly_T, *poly_tend, *node_const, *par, *t_dyn, *t_rom, *t_data;
-  const int *node_var, *itab, *ent_ptr;
+  const double *poly_T, *poly_tend, *node_const, *par, *t_dyn, *t_rom, *t_data, *dur0;
+  const int *node_var, *itab, *ent_ptr, *poly_ph;
+  int* ent_col;              // Jacobian slot columns (written here once the durations move: dyn)
   const ChdSet* sets;
-  int Pmax, F_max;
+  int Pmax, F_max, Ph_max;
+  int dyn;                   // polynomial boundaries are run-time data: node columns of the located blocks are re-assigned
+  int opt_dur;               // stage 3: derivatives with respect to the switch times are wanted
 };
 
 __device__ __forceinline__ void chd_make_ctx(const ChdDev& D, int b, const double* x, ChdCtx& c) {
@@ -22,6 +25,12 @@ __device__ __forceinline__ void chd_make_ctx(const ChdDev& D, int b, const doubl
   c.x = x;
   c.poly_T = D.poly_T + (size_t)b * D.S * D.Pmax;
   c.poly_tend = D.poly_tend + (size_t)b * D.S * D.Pmax;
+  c.poly_ph = D.poly_ph + (size_t)b * D.S * D.Pmax;
+  c.dur0 = D.dur0 + (size_t)b * D.n_ee_max * D.Ph_max;
+  c.ent_col = D.ent_col + (size_t)b * D.slots_max;
+  c.Ph_max = D.Ph_max;
+  c.dyn = 0;
+  c.opt_dur = 0;
   c.node_const = D.node_const + (size_t)b * D.S * (D.Pmax + 1) * 6;
   c.node_var = D.node_var + (size_t)b * D.S * (D.Pmax + 1) * 6;
   c.par = D.par + (size_t)b * D.par_stride;
@@ -39,6 +48,7 @@ __device__ __forceinline__ void chd_make_ctx(const ChdDev& D, int b, const doubl
 // slot = side*6 + nd*3 + dim  (side: start/end node, nd: 0 position / 1 velocity node value).
 struct ChdSpl {
   int poly;
+  double tl, T;              // local time and duration of the active polynomial
   ChdBasis B;
   const int* var;
   const double* cst;
@@ -47,13 +57,15 @@ __device__ __forceinline__ void chd_spl_at(const ChdCtx& c, int s, double t, Chd
   double tl;
   const int np = c.h->sp_npoly[s];
   o.poly = chd_locate(c.poly_tend + (size_t)s * c.Pmax, np, t, &tl);
-  chd_basis(tl, c.poly_T[(size_t)s * c.Pmax + o.poly], o.B);
+  o.tl = tl, o.T = c.poly_T[(size_t)s * c.Pmax + o.poly];
+  chd_basis(tl, o.T, o.B);
   o.var = c.node_var + ((size_t)s * (c.Pmax + 1) + o.poly) * 6;
   o.cst = c.node_const + ((size_t)s * (c.Pmax + 1) + o.poly) * 6;
 }
 __device__ __forceinline__ void chd_spl_poly(const ChdCtx& c, int s, int poly, double tl, ChdSpl& o) {
   o.poly = poly;
-  chd_basis(tl, c.poly_T[(size_t)s * c.Pmax + poly], o.B);
+  o.tl = tl, o.T = c.poly_T[(size_t)s * c.Pmax + poly];
+  chd_basis(tl, o.T, o.B);
   o.var = c.node_var + ((size_t)s * (c.Pmax + 1) + poly) * 6;
   o.cst = c.node_const + ((size_t)s * (c.Pmax + 1) + poly) * 6;
 }
@@ -70,6 +82,43 @@ __device__ __forceinline__ void chd_spl_val(const ChdCtx& c, const ChdSpl& o, in
 }
 // weight of slot (side, nd) for the deriv-th derivative
 __device__ __forceinline__ double chd_slot_w(const ChdSpl& o, int deriv, int slot) { return o.B.w[deriv][(slot / 6) * 2 + ((slot % 6) / 3)]; }
+
+// Derivative of the position of a phase-based spline (foot `ee`, motion or force) with respect to the two switch
+// times that bound the active phase k: tau_{k-1} (start) and tau_k (end).  With the phase durations d = D tau this
+// is towr's PhaseSpline::GetJacobianOfPosWrtDurations / PhaseDurations::GetJacobianOfPos after the
+// change of variables: the dense "every earlier phase" columns cancel and two columns remain,
+//   d p / d tau_{k-1} = -v - inner,   d p / d tau_k = inner,   inner = (dp/dT_poly - k_prev v) / n_polys.
+// va / vb: variable index of tau_{k-1} / tau_k (the slot of d_{k-1} / d_k in x), -1 when fixed (0 and T).
+struct ChdTau {
+  int va, vb;
+  double da[3], db[3];
+};
+__device__ __forceinline__ void chd_spl_tau(const ChdCtx& c, int s, int ee, const ChdSpl& o, ChdTau& u) {
+  const int info = c.poly_ph[(size_t)s * c.Pmax + o.poly];
+  const int k = info & 4095, kprev = (info >> 12) & 255, npol = info >> 20;
+  const double t = o.tl, T = o.T, iT = 1.0 / T, t2 = t * t * iT * iT, t3 = t2 * t * iT;   // (t/T)^2, (t/T)^3
+  // d(basis weight)/dT at fixed local time
+  const double wT[4] = {6.0 * (t2 - t3) * iT, 2.0 * (t2 - t3), 6.0 * (t3 - t2) * iT, t2 - 2.0 * t3};
+  double v[3];
+  chd_spl_val(c, o, 1, v);
+  const double inv = 1.0 / npol;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double dT = wT[0] * chd_nodeval(c, o, d) + wT[1] * chd_nodeval(c, o, 3 + d) + wT[2] * chd_nodeval(c, o, 6 + d) +
+                      wT[3] * chd_nodeval(c, o, 9 + d);
+    const double inner = inv * (dT - kprev * v[d]);
+    u.da[d] = -v[d] - inner;
+    u.db[d] = inner;
+  }
+  const int P = c.h->n_phases[ee];
+  u.va = k >= 1 ? c.h->dur_xoff[ee] + k - 1 : -1;
+  u.vb = k <= P - 2 ? c.h->dur_xoff[ee] + k : -1;
+}
+// columns of a located block of a phase-based spline (run-time pattern)
+__device__ __forceinline__ void chd_put_cols(const ChdCtx& c, int e0, const ChdSpl& o) {
+#pragma unroll
+  for (int q = 0; q < 12; ++q) c.ent_col[e0 + q] = o.var[q];
+}
 
 __device__ __forceinline__ int chd_frame_index(const ChdSeq* h, double t) {  // humanoid_rigid_body_dynamics.cpp:81-87
   int idx = (int)((t / h->T) * h->F);
@@ -193,6 +242,18 @@ __device__ void chd_item_rom(const ChdCtx& c, const ChdSet& st, int k, double* g
       J[12 + q] = -chd_slot_w(A, 0, q) * dRh_d[dim];
       J[24 + q] = chd_slot_w(E, 0, q) * d[dim];
     }
+    if (c.dyn) {
+      const int e0 = c.ent_ptr[R];
+      chd_put_cols(c, e0 + 24, E);
+      ChdTau u;
+      u.va = u.vb = -1;
+      u.da[0] = u.da[1] = u.da[2] = u.db[0] = u.db[1] = u.db[2] = 0.0;
+      if (c.opt_dur) chd_spl_tau(c, chd_sp_motion(st.a), st.a, E, u);   // leg_length_constraint.cpp:105
+      c.ent_col[e0 + 36] = u.va, c.ent_col[e0 + 37] = u.vb;
+      J[36] = chd_dot(d, u.da), J[37] = chd_dot(d, u.db);
+    } else {
+      J[36] = J[37] = 0.0;
+    }
   }
 }
 
@@ -215,6 +276,20 @@ __device__ void chd_item_heel(const ChdCtx& c, const ChdSet& st, int k, double* 
       J[q] = chd_slot_w(Ea, 0, q) * d[q % 3];
       J[12 + q] = -chd_slot_w(Eb, 0, q) * d[q % 3];
     }
+    J[24] = J[25] = J[26] = J[27] = 0.0;
+    if (c.dyn) {
+      const int e0 = c.ent_ptr[R];
+      chd_put_cols(c, e0, Ea);
+      chd_put_cols(c, e0 + 12, Eb);
+      for (int q = 24; q < 28; ++q) c.ent_col[e0 + q] = -1;
+      if (c.opt_dur) {   // ee_dist_constraint.cpp:76,88
+        ChdTau ua, ub;
+        chd_spl_tau(c, chd_sp_motion(st.a), st.a, Ea, ua);
+        chd_spl_tau(c, chd_sp_motion(st.b), st.b, Eb, ub);
+        c.ent_col[e0 + 24] = ua.va, c.ent_col[e0 + 25] = ua.vb, c.ent_col[e0 + 26] = ub.va, c.ent_col[e0 + 27] = ub.vb;
+        J[24] = chd_dot(d, ua.da), J[25] = chd_dot(d, ua.db), J[26] = -chd_dot(d, ub.da), J[27] = -chd_dot(d, ub.db);
+      }
+    }
   }
 }
 
@@ -232,6 +307,38 @@ __device__ void chd_item_height(const ChdCtx& c, const ChdSet& st, int k, double
     double* J = Jv + c.ent_ptr[R];
 #pragma unroll
     for (int q = 0; q < 12; ++q) J[q] = chd_slot_w(E, 0, q) * c.h->normal[q % 3];
+    J[12] = J[13] = 0.0;
+    if (c.dyn) {
+      const int e0 = c.ent_ptr[R];
+      chd_put_cols(c, e0, E);
+      c.ent_col[e0 + 12] = c.ent_col[e0 + 13] = -1;
+      if (c.opt_dur) {   // height_constraint.cpp:43
+        ChdTau u;
+        chd_spl_tau(c, chd_sp_motion(st.a), st.a, E, u);
+        c.ent_col[e0 + 12] = u.va, c.ent_col[e0 + 13] = u.vb;
+        J[12] = chd_dot(c.h->normal, u.da), J[13] = chd_dot(c.h->normal, u.db);
+      }
+    }
+  }
+}
+
+// total_duration_constraint.cpp:60-82: sum of the free durations of foot st.a (= its last switch time)
+template <bool JAC>
+__device__ void chd_item_tottime(const ChdCtx& c, const ChdSet& st, double* g, double* Jv) {
+  const int ee = st.a, P = c.h->n_phases[ee];
+  double sum = 0.0;
+  for (int k = 0; k < P - 1; ++k) sum += c.x[c.h->dur_xoff[ee] + k];
+  g[st.row0] = sum;
+  if (JAC) Jv[c.ent_ptr[st.row0]] = 1.0;
+}
+// PhaseDurations lower bound as a row: d_k = tau_k - tau_{k-1} >= 0
+template <bool JAC>
+__device__ void chd_item_durpos(const ChdCtx& c, const ChdSet& st, int k, double* g, double* Jv) {
+  const int R = st.row0 + k;
+  g[R] = c.x[c.h->dur_xoff[st.a] + k];
+  if (JAC) {
+    double* J = Jv + c.ent_ptr[R];
+    J[0] = 1.0, J[1] = -1.0;
   }
 }
 
@@ -416,6 +523,34 @@ __device__ void chd_item_dyn(const ChdCtx& c, const ChdSet& st, int k, int part,
         Jl[12 + q] = dim == rr ? -chd_slot_w(Fs, 0, q) : 0.0;
       }
     }
+    // switch-time slots of this foot (humanoid_dynamic_constraint.cpp:112-118): two columns shared by the motion and
+    // the force spline (they run on the same PhaseDurations)
+    const int toff = 24 + 24 * n_ee + 2 * ee;
+    ChdTau up, uf;
+    up.va = up.vb = -1;
+    for (int q = 0; q < 3; ++q) up.da[q] = up.db[q] = uf.da[q] = uf.db[q] = 0.0;
+    if (c.dyn && c.opt_dur) {
+      chd_spl_tau(c, chd_sp_motion(ee), ee, Es, up);
+      chd_spl_tau(c, chd_sp_force(n_ee, ee), ee, Fs, uf);
+    }
+    for (int rr = 0; rr < 3; ++rr) {
+      double* Ja = Jv + c.ent_ptr[R0 + rr] + toff;
+      double* Jl = Jv + c.ent_ptr[R0 + 3 + rr] + toff;
+      Ja[0] = Sf[rr * 3] * up.da[0] + Sf[rr * 3 + 1] * up.da[1] + Sf[rr * 3 + 2] * up.da[2] +
+              Sr[rr * 3] * uf.da[0] + Sr[rr * 3 + 1] * uf.da[1] + Sr[rr * 3 + 2] * uf.da[2];
+      Ja[1] = Sf[rr * 3] * up.db[0] + Sf[rr * 3 + 1] * up.db[1] + Sf[rr * 3 + 2] * up.db[2] +
+              Sr[rr * 3] * uf.db[0] + Sr[rr * 3 + 1] * uf.db[1] + Sr[rr * 3 + 2] * uf.db[2];
+      Jl[0] = -uf.da[rr];
+      Jl[1] = -uf.db[rr];
+    }
+    if (c.dyn) {
+      for (int rr = 0; rr < 6; ++rr) {
+        const int e0 = c.ent_ptr[R0 + rr];
+        chd_put_cols(c, e0 + 24 + 24 * ee, Es);
+        chd_put_cols(c, e0 + 36 + 24 * ee, Fs);
+        c.ent_col[e0 + toff] = up.va, c.ent_col[e0 + toff + 1] = up.vb;
+      }
+    }
   }
 }
 
@@ -434,6 +569,12 @@ __device__ double chd_item_data(const ChdCtx& c, int s, int i, double w, double*
     for (int q = 0; q < 12; ++q) {
       const int v = P.var[q];
       if (v >= 0) atomicAdd(grad + v, -w * chd_slot_w(P, 0, q) * diff[q % 3]);
+    }
+    if (c.opt_dur && s >= 2) {   // data_cost.cpp:59-75: durations gradient of the foot targets
+      ChdTau u;
+      chd_spl_tau(c, s, s - 2, P, u);
+      if (u.va >= 0) atomicAdd(grad + u.va, -w * chd_dot(diff, u.da));
+      if (u.vb >= 0) atomicAdd(grad + u.vb, -w * chd_dot(diff, u.db));
     }
   }
   return 0.5 * w * chd_dot(diff, diff);
@@ -457,8 +598,64 @@ __device__ double chd_item_smooth(const ChdCtx& c, int s, int i, int deriv, doub
       if (v1 >= 0) atomicAdd(grad + v1, w * chd_slot_w(P1, deriv, q) * diff[q % 3]);
       if (v0 >= 0) atomicAdd(grad + v0, -w * chd_slot_w(P0, deriv, q) * diff[q % 3]);
     }
+    if (c.opt_dur && s >= 2 && deriv == 0) {   // vel_smooth_cost.cpp:56-70 (positions only: :72-79 throws for velocities)
+      ChdTau u1, u0;
+      chd_spl_tau(c, s, s - 2, P1, u1);
+      chd_spl_tau(c, s, s - 2, P0, u0);
+      if (u1.va >= 0) atomicAdd(grad + u1.va, w * chd_dot(diff, u1.da));
+      if (u1.vb >= 0) atomicAdd(grad + u1.vb, w * chd_dot(diff, u1.db));
+      if (u0.va >= 0) atomicAdd(grad + u0.va, -w * chd_dot(diff, u0.da));
+      if (u0.vb >= 0) atomicAdd(grad + u0.vb, -w * chd_dot(diff, u0.db));
+    }
   }
   return 0.5 * w * chd_dot(diff, diff);
+}
+
+// DurationCost (duration_cost.cpp:25-50), term k of foot ee: 1/2 w (d0_k - d_k)^2; gradient in switch-time space
+// (tau_k collects +g_k, tau_{k-1} collects -g_k)
+template <bool GRAD>
+__device__ double chd_item_durcost(const ChdCtx& c, int ee, int k, double w, double* grad) {
+  const int v = c.h->dur_xoff[ee] + k;
+  const double diff = c.dur0[(size_t)ee * c.Ph_max + k] - c.x[v];
+  if (GRAD) {
+    atomicAdd(grad + v, -w * diff);
+    if (k > 0) atomicAdd(grad + v - 1, w * diff);
+  }
+  return 0.5 * w * diff * diff;
+}
+
+// Spline tables of one sequence from the phase durations held in x (stage 3 onwards; before that the host-built
+// tables are exact).  Same arithmetic as towr: last duration = total - sum of the free ones (PhaseDurations),
+// polynomial duration = phase duration / polynomials in the phase, end times accumulated sequentially.
+// One thread per phase-based spline plus one per foot for the phase end times; the caller synchronises.
+__device__ __forceinline__ void chd_tables_from_x(const ChdCtx& c, const double* x, double* polyT, double* polyTend, double* phase_tend) {
+  const ChdSeq* h = c.h;
+  const int n_ee = h->n_ee;
+  for (int w = threadIdx.x; w < 3 * n_ee; w += blockDim.x) {
+    const int ee = w % n_ee, kind = w / n_ee;   // 0 motion spline, 1 force spline, 2 phase end times
+    const int P = h->n_phases[ee];
+    double sum = 0.0, tot = 0.0;
+    for (int k = 0; k < P - 1; ++k) sum += x[h->dur_xoff[ee] + k];
+    for (int k = 0; k < P; ++k) tot += c.dur0[(size_t)ee * c.Ph_max + k];
+    const double last = tot - sum;
+    if (kind == 2) {
+      if (phase_tend) {
+        double t = 0.0;
+        for (int k = 0; k < P; ++k) t += k < P - 1 ? x[h->dur_xoff[ee] + k] : last, phase_tend[(size_t)ee * c.Ph_max + k] = t;
+      }
+      continue;
+    }
+    const int s = kind == 0 ? chd_sp_motion(ee) : chd_sp_force(n_ee, ee);
+    double t = 0.0;
+    for (int j = 0; j < h->sp_npoly[s]; ++j) {
+      const int info = c.poly_ph[(size_t)s * c.Pmax + j];
+      const int ph = info & 4095, npol = info >> 20;
+      const double Tj = (ph < P - 1 ? x[h->dur_xoff[ee] + ph] : last) / npol;
+      t += Tj;
+      polyT[(size_t)s * c.Pmax + j] = Tj;
+      polyTend[(size_t)s * c.Pmax + j] = t;
+    }
+  }
 }
 
 // number of work items of a set (dynamics nodes are split in 2 + n_ee parts when the Jacobian is wanted)
@@ -490,6 +687,8 @@ __device__ void chd_eval_all(const ChdCtx& c, const ChdStageDev& sg, double* g, 
         case CHD_SET_FORCE: chd_item_force<JAC>(c, st, it, g, Jv); break;
         case CHD_SET_HEEL: chd_item_heel<JAC>(c, st, it, g, Jv); break;
         case CHD_SET_HEIGHT: chd_item_height<JAC>(c, st, it, g, Jv); break;
+        case CHD_SET_TOTTIME: chd_item_tottime<JAC>(c, st, g, Jv); break;
+        case CHD_SET_DURPOS: chd_item_durpos<JAC>(c, st, it, g, Jv); break;
       }
     }
   }
@@ -503,6 +702,10 @@ __device__ void chd_eval_all(const ChdCtx& c, const ChdStageDev& sg, double* g, 
       if (sg.w_vel[cls] != 0.0) acc += chd_item_smooth<JAC>(c, s, i, 0, sg.w_vel[cls], grad);
       if (sg.w_acc[cls] != 0.0) acc += chd_item_smooth<JAC>(c, s, i, 1, sg.w_acc[cls], grad);
     }
+  }
+  if (sg.w_dur != 0.0 && h->n_dur) {
+    for (int ee = 0, base = 0; ee < n_ee; base += h->n_phases[ee] - 1, ++ee)
+      for (int k = threadIdx.x; k < h->n_phases[ee] - 1; k += blockDim.x) acc += chd_item_durcost<JAC>(c, ee, k, sg.w_dur, grad);
   }
   red[threadIdx.x] = acc;
   __syncthreads();

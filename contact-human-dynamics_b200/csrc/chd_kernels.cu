@@ -20,6 +20,18 @@ __global__ void chd_k_stage_begin(ChdDev D) {
   const ChdStageDev sg = D.stages[D.ipm[b].stage];
   const int max_iter = sg.max_iter;
   const ChdSeq* h = D.seq + b;
+  if (sg.opt_dur && h->n_dur == 0) {
+    // more phase durations than the dense border holds (CHD_MAX_DUR): stage 3 is not attempted; like the reference
+    // after a failed stage 3 the schedule continues with the fixed-duration stage 4 (phys_optim.cpp:713-749)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      D.ipm[b].iter = 0;
+      chd_stage_advance(D, D.ipm[b], -3, sg.snap_after);
+    }
+    return;
+  }
+  // stage 3 continues from the primal-dual point stage 2.2 left behind (same rows + the duration rows)
+  const bool warm = sg.opt_dur && D.ipm[b].last_p1 == CHD_STAGE_22 + 1;
   int* rf = D.rflag + (size_t)b * D.m_max;
   const double* lo = D.row_lo + (size_t)b * D.m_max;
   const double* hi = D.row_hi + (size_t)b * D.m_max;
@@ -33,9 +45,17 @@ __global__ void chd_k_stage_begin(ChdDev D) {
         if (lo[r] > -CHD_INF) f |= CHD_ROW_HASL;
         if (hi[r] < CHD_INF) f |= CHD_ROW_HASU;
       }
+      if (warm && (rf[r] & CHD_ROW_ACTIVE)) f |= CHD_ROW_WARM;   // keeps scaling, slack and multipliers (chd_k_init)
     }
     rf[r] = f;
     D.g[(size_t)b * D.m_max + r] = 0.0;
+  }
+  if (sg.opt_dur) {
+    // from here on the spline tables follow the durations held in x (PhaseDurations::SetVariables)
+    ChdCtx c;
+    chd_make_ctx(D, b, D.x + (size_t)b * D.n_max, c);
+    chd_tables_from_x(c, c.x, D.poly_T + (size_t)b * D.S * D.Pmax, D.poly_tend + (size_t)b * D.S * D.Pmax,
+                      D.phase_tend + (size_t)b * D.n_ee_max * D.Ph_max);
   }
   if (threadIdx.x == 0) {
     ChdIpm& I = D.ipm[b];
@@ -44,10 +64,12 @@ __global__ void chd_k_stage_begin(ChdDev D) {
     I.nfilt = 0;
     I.ls_fail = 0;
     I.max_iter = max_iter;
-    I.mu = CHD_MU_INIT;
-    I.delta_w = CHD_DELTA_W0;
+    I.warm = warm;
+    if (sg.opt_dur) I.dyn = 1;
+    I.band_ovf = 0;
+    if (!warm) I.mu = CHD_MU_INIT, I.sf = 1.0, I.delta_w = CHD_DELTA_W0;
+    else I.delta_w = fmax(I.delta_w, CHD_DELTA_W0);
     I.mu_filter = -1.0;
-    I.sf = 1.0;
     for (int q = 0; q < 8; ++q) I.prof[q] = 0.0;
     for (int q = 40; q < 48; ++q) I.filt[q] = 0.0;
   }
@@ -69,6 +91,8 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_eval(ChdDev D) {
   __syncthreads();
   ChdCtx c;
   chd_make_ctx(D, b, xs, c);
+  c.dyn = D.ipm[b].dyn;
+  c.opt_dur = sg.opt_dur;
   chd_eval_all<true>(c, sg, D.g + (size_t)b * D.m_max, D.Jv + (size_t)b * D.slots_max, gs, D.cost + 2 * b, red);
   double* grad = D.grad + (size_t)b * D.n_max;
   for (int i = threadIdx.x; i < h->n; i += blockDim.x) grad[i] = gs[i];
@@ -88,7 +112,9 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_init(ChdDev D) {
   for (int i = threadIdx.x; i < h->n; i += blockDim.x)
     if (vk[i] >= 0) gm = fmax(gm, fabs(grad[i]));
   gm = chd_block_max(gm, red);
-  const double sf = gm > CHD_SCAL_MAX_GRAD ? CHD_SCAL_MAX_GRAD / gm : 1.0;
+  const bool warm = D.ipm[b].warm;
+  const double mu0 = D.ipm[b].mu;
+  const double sf = warm ? D.ipm[b].sf : (gm > CHD_SCAL_MAX_GRAD ? CHD_SCAL_MAX_GRAD / gm : 1.0);
   const int* ep = D.ent_ptr + (size_t)b * (D.m_max + 1);
   const int* ec = D.ent_col + (size_t)b * D.slots_max;
   const double* Jv = D.Jv + (size_t)b * D.slots_max;
@@ -96,6 +122,10 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_init(ChdDev D) {
   for (int r = threadIdx.x; r < h->m; r += blockDim.x) {
     const int f = D.rflag[ro + r];
     if (!(f & CHD_ROW_ACTIVE)) continue;
+    if (f & CHD_ROW_WARM) {   // inherited from stage 2.2: scaling, bounds, slack and multipliers stay
+      if (!(f & CHD_ROW_EQ)) nb_l += ((f & CHD_ROW_HASL) ? 1 : 0) + ((f & CHD_ROW_HASU) ? 1 : 0);
+      continue;
+    }
     double rm = 0.0;
     for (int e = ep[r]; e < ep[r + 1]; ++e) {
       const int col = ec[e];
@@ -126,8 +156,9 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_init(ChdDev D) {
       s = fmin(s, dU - pU);
     }
     D.dL[ro + r] = dL, D.dU[ro + r] = dU, D.s[ro + r] = s;
-    D.zL[ro + r] = hl ? 1.0 : 0.0;
-    D.zU[ro + r] = hu ? 1.0 : 0.0;
+    // new rows of a warm-started stage start on the central path of the inherited barrier parameter
+    D.zL[ro + r] = hl ? (warm ? mu0 / (s - dL) : 1.0) : 0.0;
+    D.zU[ro + r] = hu ? (warm ? mu0 / (dU - s) : 1.0) : 0.0;
     nb_l += (hl ? 1 : 0) + (hu ? 1 : 0);
   }
   const double nbnd = chd_block_sum((double)nb_l, red);
@@ -145,7 +176,7 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_init(ChdDev D) {
 // dynamic shared memory: xt[n_max] | red[CHD_THREADS]
 __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D) {
   extern __shared__ double sm[];
-  __shared__ int s_ok, s_ftype;
+  __shared__ int s_ok, s_ftype, s_trust;
   __shared__ double s_cost;
   const int b = blockIdx.x;
   ChdIpm& I = D.ipm[b];
@@ -167,12 +198,43 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D) {
   }
   ChdCtx c;
   chd_make_ctx(D, b, xt, c);
+  c.dyn = I.dyn;
+  c.opt_dur = sg.opt_dur;
+  if (sg.opt_dur) {   // the trial durations get their own spline tables
+    c.poly_T = D.poly_Tt + (size_t)b * D.S * D.Pmax;
+    c.poly_tend = D.poly_tendt + (size_t)b * D.S * D.Pmax;
+    const size_t cnt = (size_t)D.S * D.Pmax;
+    for (size_t i = tid; i < cnt; i += nt) {   // base splines and padding: fixed
+      D.poly_Tt[(size_t)b * cnt + i] = D.poly_T[(size_t)b * cnt + i];
+      D.poly_tendt[(size_t)b * cnt + i] = D.poly_tend[(size_t)b * cnt + i];
+    }
+    __syncthreads();
+  }
+  const double theta_ref = I.theta_ref;
   double alpha = a_pr;
   int ls = 0;
   bool accepted = false, ftype = false;
   for (ls = 0; ls < CHD_MAX_BACKTRACK; ++ls) {
     for (int i = tid; i < n; i += nt) xt[i] = x[i] + alpha * dx[i];
     __syncthreads();
+    if (sg.opt_dur) {
+      // trust region of stage 3: every switch time stays within CHD_TAU_TRUST of its input value (the band of the KKT
+      // matrix is sized for the polynomials that can reach a sample time within that distance)
+      if (tid == 0) s_trust = 0;
+      __syncthreads();
+      if (tid < h->n_ee) {
+        double t = 0.0, t0 = 0.0;
+        int bad = 0;
+        for (int k = 0; k < h->n_phases[tid] - 1; ++k) {
+          t += xt[h->dur_xoff[tid] + k];
+          t0 += c.dur0[(size_t)tid * c.Ph_max + k];
+          if (fabs(t - t0) > CHD_TAU_TRUST) bad = 1;
+        }
+        if (bad) s_trust = 1;
+      }
+      chd_tables_from_x(c, xt, D.poly_Tt + (size_t)b * D.S * D.Pmax, D.poly_tendt + (size_t)b * D.S * D.Pmax, nullptr);
+      __syncthreads();
+    }
     chd_eval_all<false>(c, sg, gt, nullptr, nullptr, &s_cost, red);
     double a_th = 0.0, a_bar = 0.0;
     for (int r = tid; r < m; r += nt) {
@@ -192,6 +254,10 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D) {
     if (tid == 0) {
       const double phit = sf * s_cost + bar_t;
       bool ok = isfinite(phit) && isfinite(theta_t) && theta_t <= I.theta_max;
+      // nonlinearity guard of stage 3: the linearised constraints predict theta(alpha) = (1 - alpha) theta; the trial
+      // point is refused while the second-order error exceeds the predicted decrease (or a small absolute level)
+      if (sg.opt_dur && s_trust) ok = false;
+      if (sg.opt_dur && ok && theta_t - (1.0 - alpha) * theta > CHD_NL_GUARD * fmax(alpha * theta, CHD_NL_FLOOR * fmax(1.0, theta_ref))) ok = false;
       for (int q = 0; ok && q < I.nfilt; ++q)
         if (theta_t >= I.filt[2 * q] && phit >= I.filt[2 * q + 1]) ok = false;
       bool acc = false, ft = false;
@@ -220,6 +286,11 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D) {
   // x was left at the accepted trial point in xt
   double* xg = D.x + vo;
   for (int i = tid; i < n; i += nt) xg[i] = xt[i];
+  if (sg.opt_dur) {
+    __syncthreads();
+    chd_tables_from_x(c, xt, D.poly_T + (size_t)b * D.S * D.Pmax, D.poly_tend + (size_t)b * D.S * D.Pmax,
+                      D.phase_tend + (size_t)b * D.n_ee_max * D.Ph_max);
+  }
   for (int r = tid; r < m; r += nt) {
     const int f = rf[r];
     if (!(f & CHD_ROW_ACTIVE)) continue;
@@ -309,6 +380,33 @@ __global__ void chd_k_snapshot(ChdDev D, int* frames_out) {
   chd_sample_seq(D, b, D.snapshots + (size_t)snap * D.B * D.fo_max * stride, frames_out);
   __syncthreads();
   if (threadIdx.x == 0) D.ipm[b].snap = -1;
+}
+
+// spline tables from the durations in x for every sequence whose durations differ from the input ones
+// (chd_phys_set_x with foreign durations); marks those sequences as run-time patterned
+__global__ void chd_k_tables(ChdDev D) {
+  const int b = blockIdx.x;
+  const ChdSeq* h = D.seq + b;
+  __shared__ int s_diff;
+  if (threadIdx.x == 0) s_diff = 0;
+  __syncthreads();
+  const double* x = D.x + (size_t)b * D.n_max;
+  for (int ee = 0; ee < h->n_ee && h->n_dur; ++ee)
+    for (int k = threadIdx.x; k < h->n_phases[ee] - 1; k += blockDim.x)
+      if (x[h->dur_xoff[ee] + k] != D.dur0[((size_t)b * D.n_ee_max + ee) * D.Ph_max + k]) s_diff = 1;
+  __syncthreads();
+  if (!s_diff && !D.ipm[b].dyn) return;
+  ChdCtx c;
+  chd_make_ctx(D, b, x, c);
+  chd_tables_from_x(c, x, D.poly_T + (size_t)b * D.S * D.Pmax, D.poly_tend + (size_t)b * D.S * D.Pmax,
+                    D.phase_tend + (size_t)b * D.n_ee_max * D.Ph_max);
+  if (threadIdx.x == 0) D.ipm[b].dyn = 1;
+}
+// back to the input durations (chd_phys_reset): the host-built tables and columns are restored by the caller
+__global__ void chd_k_clear_dyn(ChdDev D) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= D.B) return;
+  D.ipm[b].dyn = 0, D.ipm[b].last_p1 = 0;
 }
 
 // puts every sequence at the start of the schedule D.sched

@@ -19,37 +19,59 @@
 #include "chd_eval.cuh"
 #include "chd_kkt_tiles.cuh"
 
-// Gauss-Newton Hessian of a least-squares cost sample: H += wgt * sum_dim J_dim^T J_dim, where the
-// sample is a signed sum over (up to two) located polynomials of B(deriv) node values.
-__device__ void chd_hess_sample(const ChdKT& K, const int* vk, const ChdSpl* P, const double* sign, int np, int deriv, double wgt) {
-  for (int a = 0; a < np * 12; ++a) {
-    const int pa = a / 12, qa = a % 12, va = P[pa].var[qa];
-    if (va < 0) continue;
-    const int ia = vk[va];
-    if (ia < 0) continue;
-    const double wa = sign[pa] * chd_slot_w(P[pa], deriv, qa);
-    if (wa == 0.0) continue;
-    for (int bq = 0; bq < np * 12; ++bq) {
-      const int pb = bq / 12, qb = bq % 12;
-      if ((qb % 3) != (qa % 3)) continue;
-      const int vb = P[pb].var[qb];
-      if (vb < 0) continue;
-      const int ib = vk[vb];
-      if (ib < 0 || ia < ib) continue;
-      const double wb = sign[pb] * chd_slot_w(P[pb], deriv, qb);
-      if (wb != 0.0) chd_kadd(K, ia, ib, wgt * wa * wb);
+// Gauss-Newton Hessian of a least-squares cost sample: H += wgt * J^T J, where the sample residual (3 rows) is a
+// signed sum over (up to two) located polynomials of B(deriv) node values.  Every Jacobian column is a 3-vector:
+// wgt_q e_dim for a node slot, and -- stage 3, foot splines, positions -- the switch-time columns of chd_spl_tau.
+__device__ void chd_hess_sample(const ChdCtx& c, const ChdKT& K, const int* vk, int s, const ChdSpl* P, const double* sign, int np, int deriv,
+                                double wgt) {
+  int idx[28];
+  double cv[28][3];
+  int ne = 0;
+  for (int pa = 0; pa < np; ++pa) {
+    for (int qa = 0; qa < 12; ++qa) {
+      const int va = P[pa].var[qa];
+      const int ia = va >= 0 ? vk[va] : -1;
+      const double wa = sign[pa] * chd_slot_w(P[pa], deriv, qa);
+      if (ia < 0 || wa == 0.0) continue;
+      idx[ne] = ia;
+      cv[ne][0] = cv[ne][1] = cv[ne][2] = 0.0;
+      cv[ne][qa % 3] = wa;
+      ++ne;
+    }
+    if (c.opt_dur && s >= 2 && deriv == 0) {
+      ChdTau u;
+      chd_spl_tau(c, s, s - 2, P[pa], u);
+      if (u.va >= 0) {
+        idx[ne] = vk[u.va];
+        for (int d = 0; d < 3; ++d) cv[ne][d] = sign[pa] * u.da[d];
+        ++ne;
+      }
+      if (u.vb >= 0) {
+        idx[ne] = vk[u.vb];
+        for (int d = 0; d < 3; ++d) cv[ne][d] = sign[pa] * u.db[d];
+        ++ne;
+      }
     }
   }
+  for (int a = 0; a < ne; ++a)
+    for (int bq = 0; bq < ne; ++bq) {
+      if (idx[a] < idx[bq]) continue;
+      const double v = cv[a][0] * cv[bq][0] + cv[a][1] * cv[bq][1] + cv[a][2] * cv[bq][2];
+      if (v != 0.0) chd_kadd(K, idx[a], idx[bq], wgt * v);
+    }
 }
 
-__global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D) {
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  if (D.ipm[b].phase != CHD_PH_BEGIN) return;
-  const ChdStageDev sg = D.stages[D.ipm[b].stage];
+// Kbase of sequence b: Gauss-Newton Hessian of the cost terms of data_cost.cpp / vel_smooth_cost.cpp /
+// duration_cost.cpp at the current x, scaled by the objective scaling.  Constant during a fixed-duration stage (the
+// costs are quadratic in the node values); in stage 3 the basis weights move with the durations and it is rebuilt
+// every iteration.
+__device__ void chd_hess_build(const ChdDev& D, int b, const ChdStageDev& sg) {
+  const int tid = threadIdx.x, nt = blockDim.x;
   const ChdSeq* h = D.seq + b;
   ChdKT K;
   double* base = D.Kbase + (size_t)b * D.kstride;
   chd_kt_init(D, h, base, K);
+  K.ovf = &D.ipm[b].band_ovf;
   for (size_t i = tid; i < D.kstride; i += nt) base[i] = 0.0;
   __syncthreads();
   const double sf = D.ipm[b].sf;
@@ -57,33 +79,50 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D) {
   for (int i = K.Na + tid; i < K.Np; i += nt) K.band[((size_t)(i >> 3) * K.Q) * 64 + (i & 7) * 9] = 1.0;  // identity padding of the band
   ChdCtx c;
   chd_make_ctx(D, b, D.x + (size_t)b * D.n_max, c);
+  c.dyn = D.ipm[b].dyn;
+  c.opt_dur = sg.opt_dur;
   const int n_ee = h->n_ee, nsp = 2 + n_ee, F = h->F, ns = h->n_smooth;
   for (int it = tid; it < nsp * F; it += nt) {
     const int s = it / F, i = it % F, cls = s < 2 ? s : 2;
     ChdSpl P[2];
     double sgn[2] = {1.0, -1.0};
     chd_spl_at(c, s, c.t_data[i], P[1]);
-    if (sg.w_data[cls] != 0.0) chd_hess_sample(K, vk, P + 1, sgn, 1, 0, sf * sg.w_data[cls]);
+    if (sg.w_data[cls] != 0.0) chd_hess_sample(c, K, vk, s, P + 1, sgn, 1, 0, sf * sg.w_data[cls]);
     if (i < ns && (sg.w_vel[cls] != 0.0 || sg.w_acc[cls] != 0.0)) {
       chd_spl_at(c, s, c.t_data[i] + h->dt, P[0]);
-      if (sg.w_vel[cls] != 0.0) chd_hess_sample(K, vk, P, sgn, 2, 0, sf * sg.w_vel[cls]);
-      if (sg.w_acc[cls] != 0.0) chd_hess_sample(K, vk, P, sgn, 2, 1, sf * sg.w_acc[cls]);
+      if (sg.w_vel[cls] != 0.0) chd_hess_sample(c, K, vk, s, P, sgn, 2, 0, sf * sg.w_vel[cls]);
+      if (sg.w_acc[cls] != 0.0) chd_hess_sample(c, K, vk, s, P, sgn, 2, 1, sf * sg.w_acc[cls]);
     }
   }
-  __syncthreads();
-  if (tid == 0) D.ipm[b].phase = CHD_PH_RUN;
+  if (sg.opt_dur && sg.w_dur != 0.0) {   // duration_cost.cpp: w I in the durations = w D^T D in the switch times
+    for (int ee = 0; ee < n_ee; ++ee)
+      for (int k = tid; k < h->n_phases[ee] - 1; k += nt) {
+        const int i = vk[h->dur_xoff[ee] + k];
+        chd_kadd(K, i, i, sf * sg.w_dur);
+        if (k > 0) {
+          const int j = vk[h->dur_xoff[ee] + k - 1];
+          chd_kadd(K, j, j, sf * sg.w_dur);
+          chd_kadd(K, i, j, -sf * sg.w_dur);
+        }
+      }
+  }
 }
 
-// a stage ended for this sequence: record its outcome, request the snapshot, move on in the schedule
-__device__ __forceinline__ void chd_stage_advance(const ChdDev& D, ChdIpm& I, int status, int snap_after) {
-  I.st_status[I.stage] = status;
-  I.st_iters[I.stage] = I.iter;
-  I.snap = snap_after;
-  I.step_ready = 0;
-  I.kw_req = 0;
-  I.pos += 1;
-  if (I.pos < D.nsched) I.stage = D.sched[I.pos], I.phase = CHD_PH_BEGIN;
-  else I.phase = CHD_PH_FINISHED;
+__global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D) {
+  const int b = blockIdx.x;
+  if (D.ipm[b].phase != CHD_PH_BEGIN) return;
+  chd_hess_build(D, b, D.stages[D.ipm[b].stage]);
+  __syncthreads();
+  if (threadIdx.x == 0) D.ipm[b].phase = CHD_PH_RUN;
+}
+// stage 3, every iteration after the line search (side stream, before chd_k_kcopy)
+__global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_dur(ChdDev D) {
+  const int b = blockIdx.x;
+  const ChdIpm& I = D.ipm[b];
+  if (I.phase != CHD_PH_RUN || !I.kw_req) return;
+  const ChdStageDev sg = D.stages[I.stage];
+  if (!sg.opt_dur) return;
+  chd_hess_build(D, b, sg);
 }
 
 // y^+ * Jd^T Jd of the squared-distance rows (leg length, toe-heel distance) of sequence b added into K: one warp
@@ -97,11 +136,13 @@ __device__ __forceinline__ void chd_curv_rows(const ChdDev& D, int b, const ChdK
   const int* vk = D.var_kkt + vo;
   ChdCtx c;
   chd_make_ctx(D, b, D.x + vo, c);
+  c.dyn = D.ipm[b].dyn;
+  c.opt_dur = sg.opt_dur;
   for (int si = 0; si < h->nsets; ++si) {
     const ChdSet st = c.sets[si];
     if (!(sg.set_mask & CHD_MASK(st.type))) continue;
     if (st.type != CHD_SET_ROM && st.type != CHD_SET_HEEL) continue;
-    const int nslot = st.type == CHD_SET_ROM ? 36 : 24;
+    const int nslot = st.type == CHD_SET_ROM ? 38 : 28;   // node slots + the switch-time slots (stage 3)
     for (int k = wid; k < st.nitems; k += nw) {
       const int R = st.row0 + k;
       const double yc = D.sc[ro + R] * D.y[ro + R];
@@ -128,7 +169,25 @@ __device__ __forceinline__ void chd_curv_rows(const ChdDev& D, int b, const ChdK
         chd_spl_at(c, chd_sp_motion(st.a), t, P0);   // d = p_a - p_b
         chd_spl_at(c, chd_sp_motion(st.b), t, P1);
       }
+      ChdTau ua, ub;
+      ua.va = ua.vb = ub.va = ub.vb = -1;
+      if (c.opt_dur) {
+        if (st.type == CHD_SET_ROM) chd_spl_tau(c, chd_sp_motion(st.a), st.a, P2, ua);
+        else chd_spl_tau(c, chd_sp_motion(st.a), st.a, P0, ua), chd_spl_tau(c, chd_sp_motion(st.b), st.b, P1, ub);
+      }
+      const int nnode = st.type == CHD_SET_ROM ? 36 : 24;
       for (int a = lane; a < nslot; a += 32) {
+        if (a >= nnode) {   // switch-time columns: d(d)/d(tau) is the 3-vector da / db of the foot spline (second foot: minus)
+          const int t4 = a - nnode;
+          const ChdTau& u = t4 < 2 ? ua : ub;
+          const int var = (t4 & 1) ? u.vb : u.va;
+          const double* dv = (t4 & 1) ? u.db : u.da;
+          const int ia = var >= 0 ? vk[var] : -1;
+          ws[a * 5 + 0] = (double)ia;
+          ws[a * 5 + 1] = ia >= 0 ? (t4 < 2 ? 1.0 : -1.0) : 0.0;
+          ws[a * 5 + 2] = ia >= 0 ? dv[0] : 0.0, ws[a * 5 + 3] = ia >= 0 ? dv[1] : 0.0, ws[a * 5 + 4] = ia >= 0 ? dv[2] : 0.0;
+          continue;
+        }
         const int ba = a / 12, qa = a % 12, da = qa % 3;
         const ChdSpl& Pa = ba == 0 ? P0 : (ba == 1 ? P1 : P2);
         const int va = Pa.var[qa];
@@ -170,7 +229,8 @@ __device__ __forceinline__ void chd_curv_rows(const ChdDev& D, int b, const ChdK
 __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT& K, double delta_w, double mu, double sf, double* rhs_s,
                                              bool do_mat, int t0, int tstep, double* g0 = nullptr, double* g1 = nullptr) {
   const ChdSeq* h = D.seq + b;
-  const int n = h->n, m = h->m, Na = K.Na;
+  const int n = D.stages[D.ipm[b].stage].opt_dur ? h->n : h->n - h->n_dur;   // the durations are unknowns in stage 3 only
+  const int m = h->m, Na = K.Na;
   const size_t ro = (size_t)b * D.m_max, vo = (size_t)b * D.n_max;
   const int* rf = D.rflag + ro;
   const int* vk = D.var_kkt + vo;
@@ -293,22 +353,30 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   ChdKT K;
   double* kw = D.Kwork + (size_t)b * D.kstride;
   chd_kt_init(D, h, kw, K);
-  const int Q = K.Q, nbt = K.nbt, nbp8 = K.nbp8, NBR = K.nbr, nbl = h->nb, nbc = K.nbc;
+  K.ovf = &I.band_ovf;
+  if (!sg.opt_dur) K.q = D.Qfix - 1;   // fixed-duration stages: the static pattern needs fewer band tiles than stage 3 may
+  // (below, Q is the number of block rows of the elimination window of this stage, Qs the storage stride of a block column)
+  const int n_act = sg.opt_dur ? n : n - h->n_dur;          // the durations (last n_dur entries of x) are unknowns in stage 3 only
+  const int Qs = K.Q, Q = sg.opt_dur ? K.Q : D.Qfix, nbt = K.nbt, nbp8 = K.nbp8, NBR = K.nbr, nbl = sg.opt_dur ? h->nb : h->nb_fix, nbc = K.nbc;
   // WS: everything in shared memory.  !WS (long horizons / very wide bands): only the reduction buffer, the
   // corner and the panel buffers stay in shared memory; the per-unknown vectors and the window live in a global
   // (L2 resident) scratch area  vecn | xs | xs2 | win | bwin.
   const size_t n_even = (size_t)((D.n_max + 1) & ~1), xs_len = (size_t)(8 * D.nbc_max + nbp8);
   double* gs = WS ? nullptr : D.scratch + (size_t)b * D.scratch_stride;
   double* red = sm;
-  double* vecn = WS ? red + CHD_KKT_THREADS : gs;
-  double* xs = vecn + n_even;                 // keep 16-byte alignment for cp.async targets
-  double* cc = WS ? xs + xs_len : red + CHD_KKT_THREADS;
+  double* cc = red + CHD_KKT_THREADS;
   double* ypan = cc + nbp8 * nbp8;
   double* xpan = ypan + (Q + nbt) * 64;
-  double* xs2 = WS ? ypan : xs + xs_len;      // back-substitution accumulator (WS: aliases the then idle panel buffers)
   double* dinv = ypan + D.pan_doubles;
-  double* win = WS ? dinv + 16 : xs2 + 8 * (size_t)D.nbc_max;
+  // WS: the per-unknown vectors vecn (step recovery) and xs (right-hand side before, solution after the factorisation)
+  // alias the tail of the window region, which is dead whenever they are live (the right-hand side moves into the border
+  // storage before the window is loaded; the back-substitution stages its tiles in the front part only)
+  const size_t win_region = (size_t)D.win_tiles * 64 + (size_t)Qs * nbt * 64;
+  double* win = WS ? dinv + 16 : gs + n_even + xs_len + 8 * (size_t)D.nbc_max;
   double* bwin = win + (size_t)D.win_tiles * 64;
+  double* vecn = WS ? win + win_region - n_even : gs;
+  double* xs = WS ? vecn - xs_len : vecn + n_even;
+  double* xs2 = WS ? ypan : xs + xs_len;      // back-substitution accumulator (WS: aliases the then idle panel buffers)
   const double sf = I.sf;
   double mu = I.mu;
   long long tk0 = clock64();
@@ -348,13 +416,32 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   }
   __syncthreads();
   double a_dual = 0;
-  for (int i = tid; i < n; i += nt) {
-    double v = sf * grad[i];
-    for (int t = cptr[i]; t < cptr[i + 1]; ++t) {
-      const int e = cent[t];
-      v += rowv[erow[e]] * Jv[e];
+  if (!I.dyn) {
+    for (int i = tid; i < n_act; i += nt) {
+      double v = sf * grad[i];
+      for (int t = cptr[i]; t < cptr[i + 1]; ++t) {
+        const int e = cent[t];
+        v += rowv[erow[e]] * Jv[e];
+      }
+      if (vk[i] >= 0) a_dual = fmax(a_dual, fabs(v));
     }
-    if (vk[i] >= 0) a_dual = fmax(a_dual, fabs(v));
+  } else {
+    // run-time Jacobian columns (stage 3 onwards): the column index of the layout is stale, J^T y goes through
+    // reductions into a per-sequence global vector
+    double* jty = D.jty + vo;
+    for (int i = tid; i < n; i += nt) jty[i] = 0.0;
+    __syncthreads();
+    for (int r = tid; r < m; r += nt) {
+      const double ys = rowv[r];
+      if (ys == 0.0) continue;
+      for (int e = ep[r]; e < ep[r + 1]; ++e) {
+        const int col = ec[e];
+        if (col >= 0 && Jv[e] != 0.0) atomicAdd(jty + col, ys * Jv[e]);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_act; i += nt)
+      if (vk[i] >= 0) a_dual = fmax(a_dual, fabs(sf * grad[i] + jty[i]));
   }
   const double ysum = chd_block_sum(a_ysum, red), zsum = chd_block_sum(a_zsum, red);
   const double cviol = chd_block_max(a_cviol, red), theta = chd_block_sum(a_theta, red);
@@ -389,7 +476,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     if (!done) {
       I.mu = mu;
       I.tau = fmax(CHD_TAU_MIN, 1.0 - mu);
-      if (I.iter == 0) I.theta_max = 1e4 * fmax(1.0, theta), I.theta_min = 1e-4 * fmax(1.0, theta);
+      if (I.iter == 0) I.theta_max = 1e4 * fmax(1.0, theta), I.theta_min = 1e-4 * fmax(1.0, theta), I.theta_ref = theta;
       if (mu != I.mu_filter) I.nfilt = 0, I.mu_filter = mu;
       I.theta0 = theta;
     }
@@ -449,7 +536,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   if (WS) {
     for (int idx = tid; idx < Q * Q * 64; idx += nt) {
       const int e = idx & 63, pr = idx >> 6, J = pr / Q, t = pr % Q;
-      if (J + t < Q && J < nbc && J + t < nbc) win[chd_win_slot(J + t, J, Q) * 64 + e] = K.band[((size_t)J * Q + t) * 64 + e];
+      if (J + t < Q && J < nbc && J + t < nbc) win[chd_win_slot(J + t, J, Q) * 64 + e] = K.band[((size_t)J * Qs + t) * 64 + e];
     }
     for (int idx = tid; idx < Q * nbt * 64; idx += nt) {
       const int J = idx / (nbt * 64);
@@ -485,12 +572,12 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     const int* rs = s_rs[cur];
     // tile addresses: circular triangular window in shared memory, or in place in the global band / border storage
     auto band_tile = [&](int gi, int gj) -> double* {     // tile (Kc+1+gi, Kc+1+gj), gi >= gj
-      return WS ? win + (size_t)tri(rs[gi], rs[gj]) * 64 : K.band + ((size_t)(Kc + 1 + gj) * Q + (gi - gj)) * 64;
+      return WS ? win + (size_t)tri(rs[gi], rs[gj]) * 64 : K.band + ((size_t)(Kc + 1 + gj) * Qs + (gi - gj)) * 64;
     };
     auto bord_tile = [&](int bi, int gj) -> double* {     // border tile bi of block column Kc+1+gj
       return WS ? bwin + ((size_t)rs[gj] * nbt + bi) * 64 : K.bord + ((size_t)(Kc + 1 + gj) * nbt + bi) * 64;
     };
-    double* Tkk = WS ? win + (size_t)tri(kslot, kslot) * 64 : K.band + (size_t)Kc * Q * 64;
+    double* Tkk = WS ? win + (size_t)tri(kslot, kslot) * 64 : K.band + (size_t)Kc * Qs * 64;
     double* Bk = WS ? bwin + (size_t)kslot * nbt * 64 : K.bord + (size_t)Kc * nbt * 64;
     const double* dv = dinv + 8 * cur;
     // (b) panel: Y = A L0^-T = A W^T (W = L0^-1 from the diagonal-tile factorisation) as one tensor-core product per
@@ -505,7 +592,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       for (int g = warp; g < tq + nbt; g += nwarp) {
         const bool band_t = g < tq;
         const int pg = band_t ? g : GB + (g - tq);                   // group id inside the panel buffers
-        const double* A = band_t ? (WS ? win + (size_t)tri(rs[g], kslot) * 64 : K.band + ((size_t)Kc * Q + 1 + g) * 64) : Bk + (g - tq) * 64;
+        const double* A = band_t ? (WS ? win + (size_t)tri(rs[g], kslot) * 64 : K.band + ((size_t)Kc * Qs + 1 + g) * 64) : Bk + (g - tq) * 64;
         const double ax = A[r * 8 + k], ay = A[r * 8 + k + 4];
         double c0 = 0.0, c1 = 0.0;
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -517,14 +604,14 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
         const double x0 = c0 * d0, x1 = c1 * d1;
         ypan[pg * 64 + f0] = c0, ypan[pg * 64 + f1] = c1;
         xpan[pg * 64 + f0] = x0, xpan[pg * 64 + f1] = x1;
-        double* G = band_t ? K.band + ((size_t)Kc * Q + 1 + g) * 64 : K.bord + ((size_t)Kc * nbt + (g - tq)) * 64;
+        double* G = band_t ? K.band + ((size_t)Kc * Qs + 1 + g) * 64 : K.bord + ((size_t)Kc * nbt + (g - tq)) * 64;
         *reinterpret_cast<double2*>(G + r * 8 + 2 * k) = make_double2(x0, x1);
         const bool nz = __any_sync(0xffffffffu, x0 != 0.0 || x1 != 0.0);
         if (lane == 0 && nz) s_gnz[cur][pg] = 1;
       }
     }
     if (WS)
-      for (int e = tid; e < 64; e += nt) K.band[(size_t)Kc * Q * 64 + e] = Tkk[e];
+      for (int e = tid; e < 64; e += nt) K.band[(size_t)Kc * Qs * 64 + e] = Tkk[e];
     __syncthreads();
     // (c) stream in block row Kc + Q (its slots are dead now), trailing updates on the fp64 tensor core;
     //     warp 0 takes the pair that completes the next diagonal tile and factors it right away
@@ -538,7 +625,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
         if (tile < Q) {
           const int J = tile < GB ? Kc + 1 + tile : In;
           double* dst = tile < GB ? win + (size_t)tri(kslot, rs[tile]) * 64 : Tkk;
-          chd_copy16(dst + off, K.band + ((size_t)J * Q + (In - J)) * 64 + off, WS);
+          chd_copy16(dst + off, K.band + ((size_t)J * Qs + (In - J)) * 64 + off, WS);
         } else {
           chd_copy16(Bk + (tile - Q) * 64 + off, K.bord + (size_t)In * nbt * 64 + (tile - Q) * 64 + off, WS);
         }
@@ -796,7 +883,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     // sequential anyway; without block barriers a block row costs ~0.5 k cycles instead of 1.4 k) while the other
     // warps prefetch the next chunk; one barrier per chunk.
     const int per = Q * 64;
-    const int R = max(1, (D.win_tiles + Q * nbt) / (2 * Q));
+    const int R = max(1, (int)((win_region - (WS ? n_even + xs_len : 0)) / 64) / (2 * Q));
     double* stg = win;
     auto stage_chunk = [&](int Ktop, int buf, int t0, int tstep) {   // block rows Ktop, Ktop-1, ... (R of them)
       for (int idx = t0; idx < R * Q * 32; idx += tstep) {
@@ -806,7 +893,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
         const int tile = rem >> 5, off = (rem & 31) * 2;
         const int J = tile == 0 ? Kr : Kr - tile;     // tile 0: diagonal; tile g+1: (Kr, Kr-1-g)
         if (J < 0) continue;
-        chd_copy16(stg + ((size_t)buf * R + rr) * per + tile * 64 + off, K.band + ((size_t)J * Q + (Kr - J)) * 64 + off, WS);
+        chd_copy16(stg + ((size_t)buf * R + rr) * per + tile * 64 + off, K.band + ((size_t)J * Qs + (Kr - J)) * 64 + off, WS);
       }
     };
     stage_chunk(nbc - 1, 0, tid, nt);
@@ -853,6 +940,13 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     }
   }
   CHD_PROF(5);
+  if (I.band_ovf) {
+    // a coupling left the band (stage 3 moved a polynomial boundary further than the layout allows): the stage fails and
+    // the schedule goes on with the fixed-duration stage 4, as the reference does after a failed stage 3
+    __syncthreads();
+    if (tid == 0) I.status = -2, chd_stage_advance(D, I, -2, sg.snap_after);
+    return;
+  }
   if (s_fail) {
     // numerical breakdown: raise the primal regularisation and retry next iteration (no step is taken)
     if (tid == 0) {
@@ -873,11 +967,15 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   double* dx = D.dx + vo;
   for (int i = tid; i < n; i += nt) {
     const int k = vk[i];
-    const double v = k >= 0 ? sol[k] : 0.0;
+    const double v = (k >= 0 && i < n_act) ? sol[k] : 0.0;
     dx[i] = v;
-    vecn[i] = v;
+    vecn[i] = v;   // step in the unknowns (switch times for the durations): what the Jacobian columns refer to
   }
   __syncthreads();
+  if (sg.opt_dur) {   // the line search moves x, i.e. phase durations: dd_k = dtau_k - dtau_{k-1}
+    for (int ee = 0; ee < h->n_ee; ++ee)
+      for (int k = 1 + tid; k < h->n_phases[ee] - 1; k += nt) dx[h->dur_xoff[ee] + k] = vecn[h->dur_xoff[ee] + k] - vecn[h->dur_xoff[ee] + k - 1];
+  }
   double a_pr = 1.0, a_du = 1.0, a_dphi = 0.0, a_phi = 0.0;
   for (int i = tid; i < n; i += nt) a_dphi += sf * grad[i] * vecn[i];
   for (int r = tid; r < m; r += nt) {
@@ -956,6 +1054,7 @@ __global__ void __launch_bounds__(256) chd_k_curv(ChdDev D) {
   if (!I.kw_req || I.phase != CHD_PH_RUN) return;
   ChdKT K;
   chd_kt_init(D, D.seq + b, D.Kwork + (size_t)b * D.kstride, K);
+  K.ovf = &D.ipm[b].band_ovf;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   chd_curv_rows(D, b, K, D.stages[I.stage], blockIdx.x * 8 + warp, gridDim.x * 8, lane, s_ws + warp * 192);
 }
@@ -969,6 +1068,7 @@ __global__ void __launch_bounds__(256) chd_k_asm(ChdDev D) {
   if (!I.kw_req || I.phase != CHD_PH_RUN) return;
   ChdKT K;
   chd_kt_init(D, D.seq + b, D.Kwork + (size_t)b * D.kstride, K);
+  K.ovf = &D.ipm[b].band_ovf;
   const size_t go = (size_t)b * (D.Na_max + D.nb_max);
   chd_assemble(D, b, K, I.delta_w, I.mu, I.sf, nullptr, true, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, D.rhs0 + go, D.rhs1 + go);
 }

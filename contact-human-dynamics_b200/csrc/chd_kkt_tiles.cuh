@@ -17,6 +17,7 @@
 struct ChdKT {
   int Na, Np, nbc, q, Q, nbt, nbp8, nbr;
   double *band, *bord, *corn;
+  int* ovf;   // set when a coupling falls outside the band (run-time patterns of stage 3), nullptr: not checked
 };
 
 __device__ __forceinline__ void chd_kt_init(const ChdDev& D, const ChdSeq* h, double* base, ChdKT& K) {
@@ -28,6 +29,7 @@ __device__ __forceinline__ void chd_kt_init(const ChdDev& D, const ChdSeq* h, do
   K.nbt = D.nbt;
   K.nbp8 = 8 * D.nbt;
   K.nbr = D.nb_max;
+  K.ovf = nullptr;
   K.band = base;
   K.bord = base + (size_t)D.nbc_max * D.Q * 64;
   K.corn = K.bord + (size_t)D.nbc_max * D.nbt * 64;
@@ -38,6 +40,10 @@ __device__ __forceinline__ void chd_kadd(const ChdKT& K, int i, int j, double v)
   if (i < j) { int t = i; i = j; j = t; }
   if (i < K.Na) {
     const int J = j >> 3;
+    if ((i >> 3) - J > K.q) {   // outside the band the layout sized: only possible once stage 3 has moved a polynomial boundary far
+      if (K.ovf) *K.ovf = 1;
+      return;
+    }
     atomicAdd(K.band + ((size_t)J * K.Q + ((i >> 3) - J)) * 64 + (i & 7) * 8 + (j & 7), v);
   } else if (j < K.Na) {
     const int b = i - K.Na;

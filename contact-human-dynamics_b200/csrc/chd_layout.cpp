@@ -6,6 +6,8 @@
 #include <thread>
 #include <cmath>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 namespace {
@@ -72,7 +74,7 @@ struct SeqBuild {
   ChdSeq h;
   std::vector<SplineBuild> sp;
   std::vector<double> x0, t_dyn, t_rom, t_data, row_lo, row_hi, var_t0, var_t1, row_t;
-  std::vector<char> var_fixed, var_stance;
+  std::vector<char> var_fixed, var_stance, var_dur;
   std::vector<ChdSet> sets;
   std::vector<int> itab, ent_ptr, ent_col, var_kkt, row_kkt, row_set;
 };
@@ -246,6 +248,20 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
     }
     S.nvar = xoff - S.xoff;
   }
+  // phase durations (nlp_formulation.cpp:188-203; stacked after the node sets, phys_optim.cpp:680-681): P - 1 free
+  // durations per foot.  They are variables of stage 3 only; the other stages keep them fixed.
+  sb.var_dur.assign(sb.x0.size(), 0);
+  {
+    int nd = 0;
+    for (int ee = 0; ee < n_ee; ++ee) nd += P[ee] - 1;
+    h.n_dur = nd <= CHD_MAX_DUR ? nd : 0;
+    for (int ee = 0; ee < n_ee; ++ee) {
+      h.dur_xoff[ee] = xoff;
+      if (!h.n_dur) continue;
+      for (int k = 0; k < P[ee] - 1; ++k)
+        sb.x0.push_back(dur[ee][k]), sb.var_fixed.push_back(0), sb.var_stance.push_back(0), sb.var_dur.push_back(1), xoff++;
+    }
+  }
   h.n = xoff;
   for (int s = 0; s < h.n_splines; ++s) h.sp_npoly[s] = sb.sp[s].npoly(), h.sp_xoff[s] = sb.sp[s].xoff, h.sp_nvar[s] = sb.sp[s].nvar;
 
@@ -266,6 +282,8 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
       }
     }
   }
+  for (int v = 0; v < h.n; ++v)
+    if (sb.var_dur[v]) sb.var_t0[v] = 0.0, sb.var_t1[v] = T;
   // time tables
   sb.t_dyn = discretize(T, 0.1);   // parameters.cpp:58-59 (dynamic and height share dt = 0.1)
   sb.t_rom = discretize(T, 0.08);  // parameters.cpp:57
@@ -305,6 +323,10 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
     add_set(CHD_SET_HEEL, 1, 3, h.n_rom, 0);
   }
   for (int ee = 0; ee < n_ee; ++ee) add_set(CHD_SET_HEIGHT, ee, 0, h.n_dyn, 0);
+  if (h.n_dur) {  // stage 3 only (phys_optim.cpp:667-679): total-duration rows, duration bounds as rows
+    for (int ee = 0; ee < n_ee; ++ee) add_set(CHD_SET_TOTTIME, ee, 0, 1, 0);
+    for (int ee = 0; ee < n_ee; ++ee) add_set(CHD_SET_DURPOS, ee, 0, P[ee] - 1, 0);
+  }
   h.m = row;
   h.nsets = (int)sb.sets.size();
 
@@ -315,17 +337,37 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
   sb.row_set.assign(h.m, 0);
   sb.ent_ptr.assign(h.m + 1, 0);
   sb.ent_col.clear();
+  // In stage 3 the polynomial boundaries of the phase-based splines move with the durations, so the polynomial active
+  // at a fixed sample time can change: the node columns of those blocks are re-assigned at run time (chd_k_eval), and
+  // the bandwidth below is sized for the neighbouring polynomials too (row_ext = their extra nodes).
+  std::vector<std::vector<int>> row_ext(h.m);
+  int cur_row = 0;
+  const double margin = CHD_TAU_TRUST;   // [s] how far stage 3 may move a polynomial boundary before a coupling can leave the band
+  auto ext_nodes = [&](int s, int poly, double t, std::vector<int>& out) {
+    if (s < 2 || !h.n_dur) return;
+    auto put = [&](int node) {
+      for (int q = 0; q < 6; ++q) out.push_back(sb.sp[s].var[node * 6 + q]);
+    };
+    for (int pp = poly - 1; pp >= 0 && tend[s][pp] > t - margin; --pp) put(pp);                                  // earlier polynomials that end within the margin
+    for (int pp = poly + 1; pp < sb.sp[s].npoly() && tend[s][pp - 1] < t + margin; ++pp) put(pp + 1);            // later ones that start within it
+  };
   auto block = [&](int s, double t) {  // 12 slots: side x (pos,vel) x dim of the polynomial active at t
     double tl;
     int poly = chd_locate(tend[s].data(), sb.sp[s].npoly(), t, &tl);
     for (int side = 0; side < 2; ++side)
       for (int q = 0; q < 6; ++q) sb.ent_col.push_back(sb.sp[s].var[(poly + side) * 6 + q]);
+    ext_nodes(s, poly, t, row_ext[cur_row]);
+  };
+  // switch-time slots of the feet a time-located row touches: two per foot, columns assigned at run time in stage 3
+  auto tau_slots = [&](int feet) {
+    for (int q = 0; q < 2 * feet; ++q) sb.ent_col.push_back(-1);
   };
   for (const ChdSet& st : sb.sets) {
     const int rpi = chd_rows_per_item(st.type);
     for (int it = 0; it < st.nitems; ++it)
       for (int r = 0; r < rpi; ++r) {
         const int R = st.row0 + it * rpi + r;
+        cur_row = R;
         sb.row_set[R] = st.type;
         sb.ent_ptr[R] = (int)sb.ent_col.size();
         switch (st.type) {
@@ -348,6 +390,7 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
             const double t = sb.t_rom[it];
             sb.row_t[R] = t;
             block(0, t), block(1, t), block(chd_sp_motion(st.a), t);
+            tau_slots(1);
             const double L = st.a < 2 ? h.max_leg : h.max_heel;  // leg_length_constraint.cpp:21-27
             sb.row_lo[R] = 0.0, sb.row_hi[R] = 0.5 * L * L;
             break;
@@ -357,6 +400,7 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
             sb.row_t[R] = t;
             block(0, t), block(1, t);
             for (int ee = 0; ee < n_ee; ++ee) block(chd_sp_motion(ee), t), block(chd_sp_force(n_ee, ee), t);
+            tau_slots(n_ee);
             break;
           }
           case CHD_SET_FORCE: {
@@ -373,6 +417,7 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
             const double t = sb.t_rom[it];
             sb.row_t[R] = t;
             block(chd_sp_motion(st.a), t), block(chd_sp_motion(st.b), t);
+            tau_slots(2);
             sb.row_lo[R] = sb.row_hi[R] = 0.5 * h.heel_dist * h.heel_dist;
             break;
           }
@@ -380,6 +425,20 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
             const double t = sb.t_dyn[it];
             sb.row_t[R] = t;
             block(chd_sp_motion(st.a), t);
+            tau_slots(1);
+            sb.row_lo[R] = 0.0, sb.row_hi[R] = 1e20;
+            break;
+          }
+          case CHD_SET_TOTTIME: {  // sum of the free durations = last switch time (total_duration_constraint.cpp:60-82)
+            sb.row_t[R] = T;
+            sb.ent_col.push_back(h.dur_xoff[st.a] + P[st.a] - 2);
+            sb.row_lo[R] = std::max(0.0, T - 500.0), sb.row_hi[R] = T - 0.0;   // parameters.cpp:60 bounds (0, 500)
+            break;
+          }
+          case CHD_SET_DURPOS: {   // d_k = tau_k - tau_{k-1} >= 0
+            sb.row_t[R] = T;
+            sb.ent_col.push_back(h.dur_xoff[st.a] + it);
+            sb.ent_col.push_back(it > 0 ? h.dur_xoff[st.a] + it - 1 : -1);
             sb.row_lo[R] = 0.0, sb.row_hi[R] = 1e20;
             break;
           }
@@ -404,23 +463,30 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
     sb.var_kkt.assign(h.n, -1);
     sb.row_kkt.assign(h.m, -1);
     for (int v = 0; v < h.n; ++v) {
-      if (sb.var_fixed[v]) continue;
+      if (sb.var_fixed[v] || sb.var_dur[v]) continue;
       if (sb.var_stance[v] && sb.var_t1[v] - sb.var_t0[v] > span_max) border.push_back(v);
       else keys.push_back({0.5 * (sb.var_t0[v] + sb.var_t1[v]), 0, v});
     }
     // rows that keep their multiplier as a KKT unknown: equalities, and inequalities with more than 12 slots
     // (leg length); the others (terrain, friction pyramid, height -- the latter is degenerate with the terrain
     // equality during stance and is numerically safer condensed) are condensed into the primal block
-    auto explicit_row = [&](int r) { return sb.row_lo[r] == sb.row_hi[r] || sb.ent_ptr[r + 1] - sb.ent_ptr[r] > 12; };
+    auto explicit_row = [&](int r) { return sb.row_lo[r] == sb.row_hi[r] || sb.ent_ptr[r + 1] - sb.ent_ptr[r] > 16; };
     for (int r = 0; r < h.m; ++r)
       if (explicit_row(r)) keys.push_back({sb.row_t[r] + 1e-6, 1, r});
     std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.t < b.t; });
     for (size_t i = 0; i < keys.size(); ++i) (keys[i].kind == 0 ? sb.var_kkt[keys[i].id] : sb.row_kkt[keys[i].id]) = (int)i;
     h.Na = (int)keys.size();
+    h.nb_fix = (int)border.size();
+    // the switch times of stage 3 influence every row of two whole phases: dense border unknowns, placed last so that
+    // the fixed-duration stages simply work with the first nb_fix border unknowns
+    for (int v = 0; v < h.n; ++v)
+      if (sb.var_dur[v]) border.push_back(v);
     h.nb = (int)border.size();
     for (int j = 0; j < h.nb; ++j) sb.var_kkt[border[j]] = h.Na + j;
-    // half bandwidth from the coupling cliques
-    int w = 0;
+    // half bandwidth from the coupling cliques: w_fix of the fixed-duration stages (the static pattern), w with the
+    // neighbouring polynomials stage 3 may move onto a sample time
+    int w = 0, w_fix = 0;
+    bool with_ext = true;
     auto span = [&](const int* cols, int cnt, int rowpos) {
       int lo = 1 << 30, hi = -1;
       for (int i = 0; i < cnt; ++i) {
@@ -430,11 +496,16 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
         lo = std::min(lo, k), hi = std::max(hi, k);
       }
       if (rowpos >= 0) lo = std::min(lo, rowpos), hi = std::max(hi, rowpos);
-      if (hi >= 0) w = std::max(w, hi - lo);
+      if (hi >= 0) (with_ext ? w : w_fix) = std::max(with_ext ? w : w_fix, hi - lo);
     };
+    std::vector<int> merged;
+    for (int pass = 0; pass < 2; ++pass)
     for (int r = 0; r < h.m; ++r) {
-      const int* c = sb.ent_col.data() + sb.ent_ptr[r];
-      const int cnt = sb.ent_ptr[r + 1] - sb.ent_ptr[r];
+      with_ext = pass == 1;
+      merged.assign(sb.ent_col.begin() + sb.ent_ptr[r], sb.ent_col.begin() + sb.ent_ptr[r + 1]);
+      if (with_ext) merged.insert(merged.end(), row_ext[r].begin(), row_ext[r].end());
+      const int* c = merged.data();
+      const int cnt = (int)merged.size();
       if (sb.row_kkt[r] >= 0) {  // explicit row: couples the row with each of its variables
         for (int i = 0; i < cnt; ++i) span(c + i, 1, sb.row_kkt[r]);
         if (sb.row_set[r] == CHD_SET_ROM || sb.row_set[r] == CHD_SET_HEEL) span(c, cnt, -1);  // curvature term y+ Jd^T Jd
@@ -443,21 +514,28 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
       }
     }
     // cost cliques: data samples (one polynomial) and smoothing samples (polynomials at t and t + dt)
+    for (int pass = 0; pass < 2; ++pass)
     for (int s = 0; s < 2 + n_ee; ++s) {
+      with_ext = pass == 1;
       for (int i = 0; i < F; ++i) {
-        int cols[24], cnt = 0;
+        std::vector<int> cols;
         double tl;
         int poly = chd_locate(tend[s].data(), sb.sp[s].npoly(), sb.t_data[i], &tl);
-        for (int q = 0; q < 12; ++q) cols[cnt++] = sb.sp[s].var[poly * 6 + q];
+        for (int q = 0; q < 12; ++q) cols.push_back(sb.sp[s].var[poly * 6 + q]);
+        if (with_ext) ext_nodes(s, poly, sb.t_data[i], cols);
         if (i < h.n_smooth) {
           int poly2 = chd_locate(tend[s].data(), sb.sp[s].npoly(), sb.t_data[i] + p.dt, &tl);
-          for (int q = 0; q < 12; ++q) cols[cnt++] = sb.sp[s].var[poly2 * 6 + q];
+          for (int q = 0; q < 12; ++q) cols.push_back(sb.sp[s].var[poly2 * 6 + q]);
+          if (with_ext) ext_nodes(s, poly2, sb.t_data[i] + p.dt, cols);
         }
-        span(cols, cnt, -1);
+        span(cols.data(), (int)cols.size(), -1);
       }
     }
+    w = std::max(w, w_fix);
     h.w = w;
-    const double grp = (w + 7) / 8 + 1 + (h.nb + 1 + 7) / 8;
+    h.w_fix = w_fix;
+    // scored by the fixed-duration stages (most of the iterations)
+    const double grp = (w_fix + 7) / 8 + 1 + (h.nb_fix + 1 + 7) / 8;
     return (double)((h.Na + 7) / 8) * grp * grp;
   };
   const double cand[4] = {0.15, 0.35, 0.5, 1e30};
@@ -465,6 +543,7 @@ int build_sequence(const chd_phys_problem& p, SeqBuild& sb) {
   double best_cost = 0;
   for (int ci = 0; ci < 4; ++ci) {
     const double cst = order_kkt(cand[ci]);
+    if (getenv("CHD_LAYOUT_DEBUG")) fprintf(stderr, "cand %g: Na %d nb %d/%d w %d/%d cost %g\n", cand[ci], h.Na, h.nb_fix, h.nb, h.w_fix, h.w, cst);
     if (ci == 0 || cst < 0.9 * best_cost) best = ci, best_cost = cst;   // leave the default unless clearly better
   }
   order_kkt(cand[best]);
@@ -495,7 +574,7 @@ int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys
   for (auto& sb : sbs) {
     up(hb.S, sb.h.n_splines), up(hb.n_max, sb.h.n), up(hb.m_max, sb.h.m), up(hb.slots_max, sb.h.nslots);
     up(hb.sets_max, sb.h.nsets), up(hb.tab_max, (int)sb.itab.size()), up(hb.F_max, sb.h.F), up(hb.Kd_max, sb.h.n_dyn);
-    up(hb.Kr_max, sb.h.n_rom), up(hb.Na_max, sb.h.Na), up(hb.nb_max, sb.h.nb), up(hb.w_max, sb.h.w), up(hb.n_ee_max, sb.h.n_ee);
+    up(hb.Kr_max, sb.h.n_rom), up(hb.Na_max, sb.h.Na), up(hb.nb_max, sb.h.nb), up(hb.w_max, sb.h.w), up(hb.w_fix_max, sb.h.w_fix), up(hb.n_ee_max, sb.h.n_ee);
     for (auto& s : sb.sp) up(hb.Pmax, s.npoly());
     up(hb.fo_max, (int)((sb.h.T + 1e-5) / sb.h.dt) + 1);
     for (int ee = 0; ee < sb.h.n_ee; ++ee) up(hb.Ph_max, sb.h.n_phases[ee]);
@@ -525,6 +604,8 @@ int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys
   hb.row_kkt.assign((size_t)B * hb.m_max, -1);
   hb.sets.assign((size_t)B * hb.sets_max, ChdSet{-1, 0, 0, 0, 0, 0});
   hb.phase_tend.assign((size_t)B * hb.n_ee_max * hb.Ph_max, 1e300);
+  hb.dur0.assign((size_t)B * hb.n_ee_max * hb.Ph_max, 0.0);
+  hb.poly_ph.assign((size_t)B * S * Pm, 0);
   for (int i = 0; i < B; ++i) {
     SeqBuild& sb = sbs[i];
     const chd_phys_problem& p = problems[i];
@@ -537,6 +618,8 @@ int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys
         hb.poly_T[((size_t)i * S + s) * Pm + k] = sp.T[k];
         hb.poly_tend[((size_t)i * S + s) * Pm + k] = t;
       }
+      for (int k = 0; k < (int)sp.info.size(); ++k)
+        hb.poly_ph[((size_t)i * S + s) * Pm + k] = sp.info[k].phase | (sp.info[k].poly_in_phase << 12) | (sp.info[k].n_polys << 20);
       std::copy(sp.var.begin(), sp.var.end(), hb.node_var.begin() + ((size_t)i * S + s) * (Pm + 1) * 6);
       std::copy(sp.cval.begin(), sp.cval.end(), hb.node_const.begin() + ((size_t)i * S + s) * (Pm + 1) * 6);
     }
@@ -544,7 +627,11 @@ int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys
       const double* d = p.ee_durations;
       for (int ee = 0; ee < sb.h.n_ee; ++ee) {
         double t = 0;
-        for (int k = 0; k < p.ee_n_phases[ee]; ++k) t += d[k], hb.phase_tend[((size_t)i * hb.n_ee_max + ee) * hb.Ph_max + k] = t;
+        for (int k = 0; k < p.ee_n_phases[ee]; ++k) {
+          t += d[k];
+          hb.phase_tend[((size_t)i * hb.n_ee_max + ee) * hb.Ph_max + k] = t;
+          hb.dur0[((size_t)i * hb.n_ee_max + ee) * hb.Ph_max + k] = d[k];
+        }
         d += p.ee_n_phases[ee];
       }
     }
@@ -591,9 +678,9 @@ int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys
   const unsigned ACC = CHD_MASK(CHD_SET_ACC), LEG = CHD_MASK(CHD_SET_TERRAIN) | CHD_MASK(CHD_SET_ROM),
                  HEEL = CHD_MASK(CHD_SET_HEEL), DYN = CHD_MASK(CHD_SET_DYN) | CHD_MASK(CHD_SET_FORCE),
                  HGT = CHD_MASK(CHD_SET_HEIGHT);
-  ChdStageCfg s1 = {ACC, {1.0, 1.0, 1.0}, {0.1, 0.1, 0.1}, {0, 0, 0}, 7000};
+  ChdStageCfg s1 = {ACC, {1.0, 1.0, 1.0}, {0.1, 0.1, 0.1}, {0, 0, 0}, 7000, 0.0};
   ChdStageCfg s2 = {ACC | LEG | DYN | HEEL, {wt.w_com_lin, wt.w_com_ang, wt.w_ee}, {0.001, 0.001, wt.w_smooth},
-                    {0.0001, 0.0001, 0.0001}, 7000};
+                    {0.0001, 0.0001, 0.0001}, 7000, 0.0};
   hb.stage[CHD_STAGE_11] = s1;
   hb.stage[CHD_STAGE_12] = s1;
   hb.stage[CHD_STAGE_12].set_mask = ACC | LEG | HEEL;
@@ -601,7 +688,12 @@ int chd_build_layout(const chd_phys_problem* problems, int batch, const chd_phys
   hb.stage[CHD_STAGE_22] = s2;
   hb.stage[CHD_STAGE_22].set_mask |= HGT;
   hb.stage[CHD_STAGE_22].max_iter = 2500;
-  hb.stage[CHD_STAGE_3] = hb.stage[CHD_STAGE_22];  // duration optimisation: see DESIGN.md (handled by stage 4 path)
+  // stage 3 (phys_optim.cpp:663-711): every set of 2.2 + TotalTime (+ the duration bounds as rows), no acceleration
+  // smoothing (:693, vel_smooth_cost.cpp:72-79), DurationCost (:696-703)
+  hb.stage[CHD_STAGE_3] = hb.stage[CHD_STAGE_22];
+  hb.stage[CHD_STAGE_3].set_mask |= CHD_MASK(CHD_SET_TOTTIME) | CHD_MASK(CHD_SET_DURPOS);
+  for (int q = 0; q < 3; ++q) hb.stage[CHD_STAGE_3].w_acc[q] = 0.0;
+  hb.stage[CHD_STAGE_3].w_dur = wt.w_dur;
   hb.stage[CHD_STAGE_3].max_iter = 2000;
   hb.stage[CHD_STAGE_4] = hb.stage[CHD_STAGE_22];
   hb.stage[CHD_STAGE_4].max_iter = 7000;

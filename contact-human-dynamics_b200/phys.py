@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 STAGES = {"1.1": 0, "1.2": 1, "2.1": 2, "2.2": 3, "3": 4, "4": 5}
-SET_NAMES = {0: "acc", 1: "terrain", 2: "rom", 3: "dyn", 4: "force", 5: "heel", 6: "height"}
+SET_NAMES = {0: "acc", 1: "terrain", 2: "rom", 3: "dyn", 4: "force", 5: "heel", 6: "height", 7: "tottime", 8: "durpos"}
 
 
 class _Problem(C.Structure):
@@ -49,7 +49,8 @@ class _Dims(C.Structure):
 EXPORTS = ["chd_version", "chd_phys_batch_create", "chd_phys_batch_destroy", "chd_phys_get_dims", "chd_phys_get_sizes",
            "chd_phys_get_x", "chd_phys_set_x", "chd_phys_eval", "chd_phys_get_layout", "chd_phys_solve_stage",
            "chd_phys_solve", "chd_phys_sample", "chd_phys_sample_device", "chd_phys_launch_count",
-           "chd_phys_kernel_times", "chd_phys_set_timing", "chd_phys_h2d_bytes", "chd_phys_reset", "chd_measure_fp64_peak", "chd_phys_get_slot_index"]
+           "chd_phys_kernel_times", "chd_phys_set_timing", "chd_phys_h2d_bytes", "chd_phys_reset", "chd_measure_fp64_peak", "chd_phys_get_slot_index", "chd_phys_get_ent_col",
+           "chd_phys_get_duals", "chd_phys_stage_stats"]
 
 
 def measure_fp64_peak():
@@ -97,6 +98,10 @@ def load_lib():
         L.chd_phys_h2d_bytes.argtypes = [vp]
         L.chd_phys_h2d_bytes.restype = C.c_int64
         L.chd_phys_reset.argtypes = [vp]
+        L.chd_phys_get_ent_col.argtypes = [vp, vp]
+        L.chd_phys_get_duals.argtypes = [vp] * 7
+        L.chd_phys_stage_stats.argtypes = [vp, vp]
+        L.chd_phys_get_slot_index.argtypes = [vp] * 4
         _LIB = L
     return _LIB
 
@@ -113,31 +118,38 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
+def make_problem_array(problems):
+    """ctypes array of `chd_phys_problem` for a list of PhysProblem + the numpy buffers it points into."""
+    B = len(problems)
+    arr = (_Problem * B)()
+    keep = []
+    for i, p in enumerate(problems):
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        k = [f64(p.hip_left), f64(p.hip_right), f64(p.inertia), f64(p.base_lin), f64(p.base_ang), f64(p.ee_pos),
+             np.ascontiguousarray(p.ee_start_contact, dtype=np.int32),
+             np.ascontiguousarray([len(d) for d in p.ee_durations], dtype=np.int32),
+             f64(np.concatenate([np.asarray(d, dtype=np.float64) for d in p.ee_durations]))]
+        keep.append(k)
+        q = arr[i]
+        q.n_frames, q.n_ee, q.dt = p.n_frames, p.n_ee, p.dt
+        q.hip_left, q.hip_right, q.inertia = _dp(k[0]), _dp(k[1]), _dp(k[2])
+        q.base_lin, q.base_ang, q.ee_pos = _dp(k[3]), _dp(k[4]), _dp(k[5])
+        q.max_leg_length, q.max_heel_length, q.heel_dist, q.body_mass = (p.max_leg_length, p.max_heel_length,
+                                                                          p.heel_dist, p.body_mass)
+        for d in range(3):
+            q.floor_normal[d] = float(p.floor_normal[d])
+            q.floor_point[d] = float(p.floor_point[d])
+        q.ee_start_contact, q.ee_n_phases, q.ee_durations = _ip(k[6]), _ip(k[7]), _dp(k[8])
+    return arr, keep
+
+
 class PhysBatch:
     def __init__(self, problems: Sequence[PhysProblem], weights=(0.4, 1.7, 0.3, 0.1, 0.1), device: int = -1,
                  host_only: bool = False):
         self.L = load_lib()
         self.problems = list(problems)
         B = len(self.problems)
-        arr = (_Problem * B)()
-        self._keep = []
-        for i, p in enumerate(self.problems):
-            f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-            k = [f64(p.hip_left), f64(p.hip_right), f64(p.inertia), f64(p.base_lin), f64(p.base_ang), f64(p.ee_pos),
-                 np.ascontiguousarray(p.ee_start_contact, dtype=np.int32),
-                 np.ascontiguousarray([len(d) for d in p.ee_durations], dtype=np.int32),
-                 f64(np.concatenate([np.asarray(d, dtype=np.float64) for d in p.ee_durations]))]
-            self._keep.append(k)
-            q = arr[i]
-            q.n_frames, q.n_ee, q.dt = p.n_frames, p.n_ee, p.dt
-            q.hip_left, q.hip_right, q.inertia = _dp(k[0]), _dp(k[1]), _dp(k[2])
-            q.base_lin, q.base_ang, q.ee_pos = _dp(k[3]), _dp(k[4]), _dp(k[5])
-            q.max_leg_length, q.max_heel_length, q.heel_dist, q.body_mass = (p.max_leg_length, p.max_heel_length,
-                                                                              p.heel_dist, p.body_mass)
-            for d in range(3):
-                q.floor_normal[d] = float(p.floor_normal[d])
-                q.floor_point[d] = float(p.floor_point[d])
-            q.ee_start_contact, q.ee_n_phases, q.ee_durations = _ip(k[6]), _ip(k[7]), _dp(k[8])
+        arr, self._keep = make_problem_array(self.problems)
         w = _Weights(*[float(x) for x in weights])
         h = C.c_void_p()
         rc = self.L.chd_phys_batch_create(arr, B, C.byref(w), -2 if host_only else device, C.byref(h))
@@ -184,6 +196,26 @@ class PhysBatch:
                    row_kkt=np.zeros((B, d["m_max"]), np.int32))
         self._chk(self.L.chd_phys_get_layout(self.h, *[_ptr(out[k]) for k in ("ent_ptr", "ent_col", "row_lo", "row_hi",
                                                                               "row_set", "var_kkt", "row_kkt")]))
+        return out
+
+    def ent_col(self) -> np.ndarray:
+        """Jacobian slot columns as they stand on the device (run-time pattern once stage 3 has moved a duration)."""
+        out = np.zeros((self.B, self.dims["slots_max"]), np.int32)
+        self._chk(self.L.chd_phys_get_ent_col(self.h, _ptr(out)))
+        return out
+
+    def duals(self) -> dict:
+        """Interior-point state of the last solved stage (scaled problem), master row order."""
+        B, d = self.B, self.dims
+        out = {k: np.zeros((B, d["m_max"])) for k in ("y", "zL", "zU", "s", "row_scale")}
+        out["obj_scale"] = np.zeros(B)
+        self._chk(self.L.chd_phys_get_duals(self.h, *[_ptr(out[k]) for k in ("y", "zL", "zU", "s", "row_scale", "obj_scale")]))
+        return out
+
+    def stage_stats(self) -> np.ndarray:
+        """(6, B, 4): objective, scaled NLP error, unscaled constraint violation, unscaled dual infeasibility per stage."""
+        out = np.zeros((6, self.B, 4))
+        self._chk(self.L.chd_phys_stage_stats(self.h, _ptr(out)))
         return out
 
     def slot_index(self) -> dict:

@@ -64,7 +64,8 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
                           int32_t device, chd_phys_batch** out);
 void chd_phys_batch_destroy(chd_phys_batch* b);
 int chd_phys_get_dims(const chd_phys_batch* b, chd_phys_dims* dims);
-/* Per-sequence sizes: n (variables), m (master rows), nslots, Na, nb, w -- six int32 per sequence [host]. */
+/* Per-sequence sizes: n (variables: node values, then the P-1 free phase durations of every foot), m (master rows),
+ * nslots, Na, nb (border unknowns incl. the durations), w -- six int32 per sequence [host]. */
 int chd_phys_get_sizes(const chd_phys_batch* b, int32_t* sizes6);
 
 /* Current iterate x: batch x n_max doubles.  [host] copies (synchronous). */
@@ -88,6 +89,22 @@ int chd_phys_get_layout(const chd_phys_batch* b, int32_t* ent_ptr, int32_t* ent_
  * col_ent[batch x slots_max] (slots grouped by variable).  [host] outputs, any may be NULL. */
 int chd_phys_get_slot_index(const chd_phys_batch* b, int32_t* ent_row, int32_t* col_ptr, int32_t* col_ent);
 
+/* Jacobian slot columns as they stand on the device: equal to chd_phys_get_layout's ent_col until stage 3 moves a
+ * phase duration; from then on the polynomial active at a sample time is located at run time and the node / switch-time
+ * columns of the time-located rows are rewritten by every evaluation.  Column index of a duration variable d_k = the
+ * switch time tau_k = d_0 + ... + d_k the solver works with (derivatives are with respect to tau). [host] output. */
+int chd_phys_get_ent_col(const chd_phys_batch* b, int32_t* ent_col);
+/* Interior-point state of the last solved stage, master row order, batch x m_max each [host], any may be NULL:
+ * constraint multipliers y, bound multipliers zL / zU of the slacks, slacks s (all of the scaled problem
+ * min obj_scale * f  s.t.  row_scale * g(x) - s = 0), the row scaling and obj_scale[batch]
+ * (what IpoptCalculatedQuantities reports as the scaled multipliers; unscaled y = y * row_scale / obj_scale). */
+int chd_phys_get_duals(const chd_phys_batch* b, double* y, double* zL, double* zU, double* s, double* row_scale,
+                       double* obj_scale);
+/* Residuals of every stage of the last chd_phys_solve / chd_phys_solve_stage: stats [host] 6 x batch x 4 =
+ * objective, scaled NLP error E0 (IPOPT's overall error, tol 1e-3), unscaled max constraint violation
+ * (constr_viol_tol 1e-4), unscaled dual infeasibility. */
+int chd_phys_stage_stats(const chd_phys_batch* b, double* stats);
+
 /* Runs the interior-point solve of one stage for every sequence (warm start from the current x).
  * status[batch] [host]: 0 = converged (IPOPT "Solve_Succeeded" test), -1 = iteration cap, -2 = numerical failure.
  * iters[batch] [host], stats[batch x 8] [host]: f, E0, unscaled constraint violation, unscaled dual inf,
@@ -99,7 +116,8 @@ int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int
  * 3 x batch x frames_out_max x (6 + 7*n_ee_max) doubles = the three SaveSolution snapshots
  * (no_dynamics, dynamics, durations), frames_out[batch] [host] = frames per sequence,
  * success[batch x 2] [host] = (dynamics_succeed, durations_succeed) of success_log.txt.
- * stage_status [host, 6 x batch] / stage_iters [host, 6 x batch] may be NULL. */
+ * stage_status [host, 6 x batch] / stage_iters [host, 6 x batch] may be NULL; status -9 = stage not run (stage 4 after a
+ * successful stage 3, phys_optim.cpp:713), -3 = stage 3 not attempted (more than 96 phase durations). */
 int chd_phys_solve(chd_phys_batch* b, double* samples, int32_t* frames_out, int32_t* success,
                    int32_t* stage_status, int32_t* stage_iters);
 

@@ -47,6 +47,7 @@ int chdo_lag_hessian(void* h, const double* y, int* ri, int* ci, double* vals);
 void chdo_row_times(void* h, double* t);
 void chdo_var_times(void* h, double* t0, double* t1);
 int chdo_dur_blocks(void* h, int* off, int* cnt);
+void chdo_init_durations(void* h, double* d);   // the free durations (first P-1 of every foot) of the input contact schedule
 }
 
 namespace {
@@ -426,6 +427,9 @@ struct Solver {
     const double nl_ke = dur_vars.empty() ? 0.0 : (getenv("CHD_NL_KE") ? atof(getenv("CHD_NL_KE")) : 1.0);   // stage 3 only (CHD_NL_GUARD in chd_dev.h)
     const double nl_fl = getenv("CHD_NL_FL") ? atof(getenv("CHD_NL_FL")) : 1e-4;
     double theta_ref = 0.0;
+    const double tau_trust = getenv("CHD_TAU_TRUST") ? atof(getenv("CHD_TAU_TRUST")) : 0.04;
+    std::vector<double> x_init_dur(dur_vars.size());
+    if (!dur_vars.empty()) chdo_init_durations(h, x_init_dur.data());
     const double rt0 = getenv("CHD_RT0") ? atof(getenv("CHD_RT0")) : 0.0, rt_dec = getenv("CHD_RT_DEC") ? atof(getenv("CHD_RT_DEC")) : 3.0;
     const double rt_min = getenv("CHD_RT_MIN") ? atof(getenv("CHD_RT_MIN")) : 0.0;
     double rho_tau = dur_vars.empty() ? 0.0 : rt0;
@@ -612,6 +616,15 @@ struct Solver {
         bool okp = std::isfinite(phit) && std::isfinite(theta_t) && theta_t <= theta_max;
         // nonlinearity guard: the linearised constraints predict theta(alpha) = (1 - alpha) theta; the trial point is
         // refused while the second-order error exceeds nl_ke x the predicted decrease (or a small absolute level)
+        if (!dur_vars.empty() && okp) {   // trust region of stage 3 (CHD_TAU_TRUST in csrc/chd_core.h): switch times within 0.04 s of the input
+          double t = 0, t0 = 0;
+          for (size_t i = 0; i < dur_vars.size(); ++i) {
+            const int j = dur_vars[i];
+            if (durk[j] == 0) t = 0, t0 = 0;
+            t += xt[j], t0 += x_init_dur[i];
+            if (std::fabs(t - t0) > tau_trust) okp = false;
+          }
+        }
         if (nl_ke > 0.0 && okp && theta_t - (1.0 - alpha) * theta > nl_ke * std::max(alpha * theta, nl_fl * std::max(1.0, theta_ref))) okp = false, nl_rej++;
         for (auto& e : filt)
           if (okp && theta_t >= e.first && phit >= e.second) okp = false;

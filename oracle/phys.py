@@ -103,6 +103,7 @@ class OracleProblem:
         k = self._keep
         self.n_ee = p.n_ee
         self.F = p.n_frames
+        self.n_dur = sum(len(d) - 1 for d in p.ee_durations)
         self.h = L.chdo_create(p.n_frames, p.n_ee, p.dt, _dp(k[0]), _dp(k[1]), p.max_leg_length, p.max_heel_length,
                                p.heel_dist, p.body_mass, _dp(k[2]), _dp(k[3]), _dp(k[4]), _dp(k[5]), _dp(k[6]), _dp(k[7]),
                                _ip(k[8]), _ip(k[9]), _dp(k[10]), _dp(k[11]))
@@ -232,8 +233,11 @@ class OracleProblem:
             res.append(self.solve_stage(st)), ids.append(st)
         out["dynamics"] = self.sample()
         dyn_ok = res[3]["status"] == 0
-        res.append(self.solve_stage("3")), ids.append("3")
-        dur_ok = res[-1]["status"] == 0                      # :709
+        if self.n_dur <= 96:                                 # CHD_MAX_DUR of the product (csrc/chd_core.h): beyond it stage 3 is not attempted
+            res.append(self.solve_stage("3")), ids.append("3")
+            dur_ok = res[-1]["status"] == 0                  # :709
+        else:
+            dur_ok = False
         if not dur_ok:
             res.append(self.solve_stage("4")), ids.append("4")
             dur_ok = res[-1]["status"] == 0                  # :746

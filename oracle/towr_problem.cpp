@@ -1020,6 +1020,12 @@ int chdo_dur_blocks(void* h, int* off, int* cnt) {
   }
   return k;
 }
+void chdo_init_durations(void* h, double* d) {
+  Problem* P = (Problem*)h;
+  int k = 0;
+  for (auto& v : P->init_dur)
+    for (size_t i = 0; i + 1 < v.size(); ++i) d[k++] = v[i];
+}
 int chdo_num_constraint_sets(void* h) { return (int)((Problem*)h)->cons.size(); }
 int chdo_constraint_set_rows(void* h, int i) { return ((Problem*)h)->cons[i]->rows; }
 const char* chdo_constraint_set_name(void* h, int i) { return ((Problem*)h)->cons[i]->name.c_str(); }

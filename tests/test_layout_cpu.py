@@ -12,9 +12,15 @@ def test_layout_matches_oracle(chd, n_ee, seed):
     p = chd.synth.make_problem(seed, n_ee=n_ee)
     b = chd.phys.PhysBatch([p], host_only=True)
     o = OracleProblem(p)
+    # stage 3 (phys_optim.cpp:663-711) adds the PhaseDurations sets and the TotalTime rows; the product keeps one layout
+    # for all stages and additionally carries the duration bounds (0, 500) of parameters.cpp:60 as rows
+    o.set_stage("3")
+    n_dur = sum(len(d) - 1 for d in p.ee_durations)
+    assert b.sizes[0, 0] == o.n and b.sizes[0, 1] == o.m + n_dur
+    np.testing.assert_allclose(b.get_x()[0, :o.n], o.get_x(), rtol=0, atol=1e-14)
     o.set_stage("2.2")
-    n, m = b.sizes[0, 0], b.sizes[0, 1]
-    assert n == o.n and m == o.m
+    n, m = o.n, o.m
+    assert n == b.sizes[0, 0] - n_dur and m == b.sizes[0, 1] - n_dur - p.n_ee
     # initial point (nlp_formulation.cpp:106-203)
     x0 = b.get_x()[0, :n]
     xlo, xhi = o.var_bounds()
@@ -23,6 +29,7 @@ def test_layout_matches_oracle(chd, n_ee, seed):
     lay = b.layout()
     # fixed variables = equality-bounded ones (start / final base velocity)
     assert np.array_equal(lay["var_kkt"][0, :n] < 0, xlo == xhi)
+    assert (lay["var_kkt"][0, n:n + n_dur] >= b.sizes[0, 3]).all()      # durations: border unknowns (stage 3)
     # row bounds
     sl = chd.phys.master_row_slices(b, 0, lay)
     im, io = master_to_oracle_perm(sl, o)
@@ -38,6 +45,7 @@ def test_layout_matches_oracle(chd, n_ee, seed):
         assert theirs <= mine, (rm, ro, sorted(theirs - mine))
     # KKT ordering: unknowns are a permutation, bandwidth covers every equality coupling
     Na, nb, w = b.sizes[0, 3], b.sizes[0, 4], b.sizes[0, 5]
+    n, m = b.sizes[0, 0], b.sizes[0, 1]
     vk, rk = lay["var_kkt"][0, :n], lay["row_kkt"][0, :m]
     used = np.concatenate([vk[vk >= 0], rk[rk >= 0]])
     assert len(np.unique(used)) == len(used) == Na + nb

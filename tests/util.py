@@ -3,7 +3,7 @@ oracle's ifopt row order (which follows phys_optim.cpp's per-stage AddConstraint
 import numpy as np
 
 ORACLE_PREFIX = {"acc": "splineacc", "terrain": "terrain-", "rom": "leg-length", "dyn": "dynamic", "force": "force-",
-                 "heel": "ee-dist", "height": "height-"}
+                 "heel": "ee-dist", "height": "height-", "tottime": "contactduration-"}
 
 
 def oracle_type_blocks(o):
@@ -30,3 +30,27 @@ def master_to_oracle_perm(master_slices, o):
             im.append(np.arange(a, b))
             io.append(np.arange(oa, ob))
     return np.concatenate(im), np.concatenate(io)
+
+
+def to_tau(M, blocks):
+    """Columns (last axis) with respect to phase durations d -> columns with respect to switch times tau (d = D tau):
+    col(tau_k) = col(d_k) - col(d_{k+1}) inside every PhaseDurations block (offset, count)."""
+    M = np.array(M, dtype=float, copy=True)
+    for off, cnt in blocks:
+        for k in range(cnt - 1):
+            M[..., off + k] -= M[..., off + k + 1]
+    return M
+
+
+def duration_blocks(p, n):
+    """(offset, count) of the PhaseDurations sets of problem p inside an x of length n (they are stacked last)."""
+    cnts = [len(d) - 1 for d in p.ee_durations]
+    off = n - sum(cnts)
+    out = []
+    for c in cnts:
+        out.append((off, c))
+        off += c
+    return out
+
+
+GPU_STAGE_IDS = {"1.1": 0, "1.2": 1, "2.1": 2, "2.2": 3, "3": 4, "4": 5}
