@@ -247,27 +247,36 @@ int chd_measure_fp64_peak(double* dfma_gflops, double* dmma_gflops) {
   return 0;
 }
 
+static int batch_create_impl(const chd_phys_problem* problems, int32_t batch, const chd_phys_weights* weights, int32_t device,
+                             chd_phys_batch* b);
+
 int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const chd_phys_weights* weights, int32_t device,
                           chd_phys_batch** out) {
   if (!problems || batch <= 0 || !out) return -1;
+  chd_phys_batch* b = new chd_phys_batch();
+  std::memset(&b->D, 0, sizeof(b->D));
+  const int rc = batch_create_impl(problems, batch, weights, device, b);
+  if (rc) {
+    chd_phys_batch_destroy(b);   // single cleanup path: streams, events, pooled allocations, host buffers
+    return rc;
+  }
+  *out = b;
+  return 0;
+}
+
+static int batch_create_impl(const chd_phys_problem* problems, int32_t batch, const chd_phys_weights* weights, int32_t device,
+                             chd_phys_batch* b) {
   const bool host_only = device == -2;  // layout tables only, no CUDA call (CPU-side tests of the host logic)
   if (device >= 0) CHD_CUDA(cudaSetDevice(device));
   chd_phys_weights w = {0.4, 1.7, 0.3, 0.1, 0.1};  // phys_optim.cpp:27-31
   if (weights) w = *weights;
-  chd_phys_batch* b = new chd_phys_batch();
   int rc = chd_build_layout(problems, batch, w, b->hb);
-  if (rc) {
-    delete b;
-    return rc;
-  }
+  if (rc) return rc;
   ChdHostBatch& hb = b->hb;
   ChdDev& D = b->D;
   std::memset(&D, 0, sizeof(D));
   b->host_only = host_only;
-  if (host_only) {
-    *out = b;
-    return 0;
-  }
+  if (host_only) return 0;
   D.B = hb.B, D.S = hb.S, D.Pmax = hb.Pmax, D.n_max = hb.n_max, D.m_max = hb.m_max, D.slots_max = hb.slots_max;
   D.sets_max = hb.sets_max, D.tab_max = hb.tab_max, D.F_max = hb.F_max, D.Kd_max = hb.Kd_max, D.Kr_max = hb.Kr_max;
   D.Na_max = hb.Na_max, D.nb_max = hb.nb_max, D.w_max = hb.w_max, D.par_stride = hb.par_stride(), D.n_ee_max = hb.n_ee_max;
@@ -369,7 +378,6 @@ int chd_phys_batch_create(const chd_phys_problem* problems, int32_t batch, const
   b->allocs.push_back(b->d_stages);
   if ((rc = dev_alloc(b, 3 * B * hb.fo_max * stride, &D.snapshots))) return rc;
   CHD_CUDA(cudaStreamSynchronize(b->stream));
-  *out = b;
   return 0;
 }
 
@@ -404,6 +412,11 @@ int chd_phys_get_sizes(const chd_phys_batch* b, int32_t* s) {
     const ChdSeq& h = b->hb.seq[i];
     s[6 * i + 0] = h.n, s[6 * i + 1] = h.m, s[6 * i + 2] = h.nslots, s[6 * i + 3] = h.Na, s[6 * i + 4] = h.nb, s[6 * i + 5] = h.w;
   }
+  return 0;
+}
+int chd_phys_get_sizes_fixed(const chd_phys_batch* b, int32_t* s) {
+  if (!b || !s) return -1;
+  for (int i = 0; i < b->hb.B; ++i) s[3 * i] = b->hb.seq[i].nb_fix, s[3 * i + 1] = b->hb.seq[i].w_fix, s[3 * i + 2] = b->hb.seq[i].n_dur;
   return 0;
 }
 int chd_phys_get_x(const chd_phys_batch* b, double* x) {
@@ -498,6 +511,15 @@ int chd_phys_get_duals(const chd_phys_batch* b, double* y, double* zL, double* z
     CHD_CUDA(cudaMemcpy(ipm.data(), b->D.ipm, B * sizeof(ChdIpm), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < B; ++i) obj_scale[i] = ipm[i].sf;
   }
+  return 0;
+}
+
+/* diagnostic: line-search inputs of the last KKT solve of sequence i (a_pr, a_du, dphi, phi0, theta0, theta_ref, mu, delta_w) */
+int chd_phys_debug_ipm(const chd_phys_batch* b, int32_t i, double* out8) {
+  if (!b || !out8 || b->host_only || !b->h_ipm || i < 0 || i >= b->hb.B) return -1;
+  const ChdIpm& I = b->h_ipm[i];
+  out8[0] = I.a_pr, out8[1] = I.a_du, out8[2] = I.dphi, out8[3] = I.phi0, out8[4] = I.theta0, out8[5] = I.theta_ref, out8[6] = I.mu, out8[7] = I.delta_w;
+  for (int q = 0; q < 8; ++q) out8[8 + q] = I.dbg[q];
   return 0;
 }
 

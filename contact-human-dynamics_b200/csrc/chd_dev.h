@@ -8,6 +8,8 @@
 #define CHD_KKT_THREADS 512
 #define CHD_NL_GUARD 1.0    /* stage 3 line search: trial refused while theta_t - (1-alpha) theta > CHD_NL_GUARD * max(alpha theta, CHD_NL_FLOOR max(1, theta_ref)) */
 #define CHD_NL_FLOOR 1e-4
+#define CHD_UNOBS_EPS 1e-14 /* "sees": diagonal of the scaled cost Hessian above this (a sample sitting exactly on a node gives weights of 1e-17) */
+#define CHD_DW_UNOBS 1e-4   /* fixed Levenberg-Marquardt weight of foot-motion node values no cost sample sees (zero diagonal of the cost Hessian) */
 #define CHD_CURV_MIN 1e-8   /* multiplier threshold below which y^+ Jd^T Jd is not added (same in oracle/ipm_oracle.cpp) */
 
 // row flags
@@ -36,6 +38,7 @@ struct ChdIpm {
   double mu, delta_w, sf, theta_max, theta_min, mu_filter, tau;
   double f, E0, viol_u, dual_u, compl_u;          // error measures at the current iterate
   double phi0, theta0, dphi, a_pr, a_du;          // line-search inputs produced by the KKT kernel
+  double dbg[8];                                  // diagnostics of the last line search: alpha, backtracks, theta_t, phi_t, guard / trust refusals
   double theta_ref;                               // theta at the first iteration of the stage (nonlinearity guard of stage 3)
   double filt[2 * CHD_FILT_MAX];
   double st_stat[6][4];                           // per stage at its end: f, E0 (scaled NLP error), unscaled constraint violation, unscaled dual infeasibility

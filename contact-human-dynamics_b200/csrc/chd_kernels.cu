@@ -256,8 +256,10 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D) {
       bool ok = isfinite(phit) && isfinite(theta_t) && theta_t <= I.theta_max;
       // nonlinearity guard of stage 3: the linearised constraints predict theta(alpha) = (1 - alpha) theta; the trial
       // point is refused while the second-order error exceeds the predicted decrease (or a small absolute level)
-      if (sg.opt_dur && s_trust) ok = false;
-      if (sg.opt_dur && ok && theta_t - (1.0 - alpha) * theta > CHD_NL_GUARD * fmax(alpha * theta, CHD_NL_FLOOR * fmax(1.0, theta_ref))) ok = false;
+      if (ls == 0) I.dbg[4] = 0.0, I.dbg[5] = 0.0;
+      I.dbg[0] = alpha, I.dbg[1] = ls, I.dbg[2] = theta_t, I.dbg[3] = phit;
+      if (sg.opt_dur && s_trust) ok = false, I.dbg[5] += 1.0;
+      if (sg.opt_dur && ok && theta_t - (1.0 - alpha) * theta > CHD_NL_GUARD * fmax(alpha * theta, CHD_NL_FLOOR * fmax(1.0, theta_ref))) ok = false, I.dbg[4] += 1.0;
       for (int q = 0; ok && q < I.nfilt; ++q)
         if (theta_t >= I.filt[2 * q] && phit >= I.filt[2 * q + 1]) ok = false;
       bool acc = false, ft = false;
@@ -338,9 +340,12 @@ __device__ void chd_sample_seq(const ChdDev& D, int b, double* out, int* frames_
   for (int k = 0; k < h->sp_npoly[0]; ++k) tot += c.poly_T[k];  // Spline::GetTotalTime of base_linear
   const int nf = (int)((tot + 1e-5) / h->dt) + 1;
   if (threadIdx.x == 0 && frames_out) frames_out[b] = nf;
+  // sample times: the reference accumulates t += dt; thread j reproduces the same rounding for its frames by
+  // continuing its own accumulation (frames i, i + blockDim, ...) from a prefix it sums once
+  double t = 0.0;
+  int at = 0;
   for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-    double t = 0.0;
-    for (int q = 0; q < i; ++q) t += h->dt;  // same accumulation as the reference loop
+    for (; at < i; ++at) t += h->dt;
     if (!(t <= tot + 1e-5)) continue;
     double* o = out + ((size_t)b * D.fo_max + i) * stride;
     ChdSpl P;

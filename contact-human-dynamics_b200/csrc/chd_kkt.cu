@@ -248,9 +248,20 @@ __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT
       if (v1 != 0.0) atomicAdd(g1 + gidx(kk), v1);
     }
   };
+  // foot-motion node values that no cost sample sees (polynomials shorter than a frame): without curvature of their own
+  // the Newton step uses them as free slack and they drift by orders of magnitude, which stage 3 (where the sample
+  // times sweep over those polynomials) cannot digest.  They get a fixed Levenberg-Marquardt weight on top of the
+  // adaptive one -- what the initial scaling of IPOPT's L-BFGS matrix does for the reference.
+  const double* kb = D.Kbase + (size_t)b * D.kstride;
+  const double* kb_corn = kb + (size_t)D.nbc_max * D.Q * 64 + (size_t)D.nbc_max * D.nbt * 64;
+  const int mot_lo = h->sp_xoff[2], mot_hi = h->sp_xoff[2 + h->n_ee];
   for (int i = t0; i < n; i += tstep) {
     const int k = vk[i];
     if (k < 0) continue;
+    if (do_mat && i >= mot_lo && i < mot_hi) {
+      const double hd = k < Na ? kb[((size_t)(k >> 3) * K.Q) * 64 + (k & 7) * 9] : kb_corn[(size_t)(k - Na) * K.nbp8 + (k - Na)];
+      if (hd <= CHD_UNOBS_EPS) mat_add(k, k, CHD_DW_UNOBS);
+    }
     mat_add(k, k, delta_w);
     rhs_add(k, -sf * grad[i]);
     g_add(k, -sf * grad[i], 0.0);
@@ -379,8 +390,13 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   double* xs2 = WS ? ypan : xs + xs_len;      // back-substitution accumulator (WS: aliases the then idle panel buffers)
   const double sf = I.sf;
   double mu = I.mu;
+  // per-phase cycle counters (scripts/prof_stage.py): compiled in only with -DCHD_PROFILE (extra barriers + clock reads)
+#ifdef CHD_PROFILE
   long long tk0 = clock64();
 #define CHD_PROF(slot) do { __syncthreads(); if (tid == 0) { long long t_ = clock64(); I.prof[slot] += (double)(t_ - tk0); tk0 = t_; } } while (0)
+#else
+#define CHD_PROF(slot) do { } while (0)
+#endif
 
   // ---------------- A. error measures, convergence, barrier update ----------------
   // J^T y is gathered per variable from a column-oriented index of the Jacobian slots (no shared-memory fp64

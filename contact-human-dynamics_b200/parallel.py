@@ -52,3 +52,139 @@ def unshard(gathered: np.ndarray, shards: List[List[int]], slots: int) -> np.nda
         for k, idx in enumerate(s):
             out[idx] = gathered[r * slots + k]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The product's multi-GPU entry point: shard -> solve -> sample into the send buffer -> ONE gather -> unshard.
+# ---------------------------------------------------------------------------------------------------------------------
+N_EXTRA = 16  # per-sequence trailer of the gathered block: frames, success[2], stage_status[6], stage_iters[6], pad
+
+
+def work_estimate(problems) -> List[float]:
+    """Predicted solver work of a sequence: interior-point iterations grow with the number of contact phases (every
+    switch adds free swing / stance nodes and, in stage 3, a duration), the cost of one iteration with the frame count."""
+    return [float(p.n_frames) * float(sum(len(d) for d in p.ee_durations)) * (p.n_ee / 2.0) for p in problems]
+
+
+def frames_out(p) -> int:
+    """SaveSolution frame count of a problem (phys_optim.cpp:84: t accumulates dt while t <= T + 1e-5)."""
+    T = float(np.sum(np.asarray(p.ee_durations[0], dtype=np.float64)))
+    return int((T + 1e-5) / p.dt) + 1
+
+
+class ShardedSolver:
+    """One process per GPU (torchrun).  Every rank holds the same problem list, solves its shard on its device and
+    takes part in a single all_gather of the fixed-size result block (final SaveSolution snapshot + status trailer).
+
+    `solve_fn(problems) -> dict(final=(n, fo, stride) array, frames, success, stage_status (6,n), stage_iters (6,n))`
+    replaces the CUDA solve in the CPU (gloo) tests; the default drives `PhysBatch` on `device`."""
+
+    def __init__(self, problems, weights=(0.4, 1.7, 0.3, 0.1, 0.1), device: int = 0, rank: int = 0, world: int = 1,
+                 group=None, solve_fn=None, tensor_device=None):
+        self.problems, self.rank, self.world, self.group = list(problems), rank, world, group
+        self.shards = shard_by_work(work_estimate(self.problems), world)
+        self.slots = pad_to(self.shards)
+        self.mine = self.shards[rank]
+        self.n_ee_max = max(p.n_ee for p in self.problems)
+        self.stride = 6 + 7 * self.n_ee_max
+        self.fo = max(frames_out(p) for p in self.problems)
+        self.width = self.fo * self.stride + N_EXTRA
+        self.solve_fn = solve_fn
+        self.batch = None
+        import torch
+        if solve_fn is None:
+            from . import phys
+            self.batch = phys.PhysBatch([self.problems[i] for i in self.mine], weights=weights, device=device) if self.mine else None
+            tensor_device = tensor_device or torch.device("cuda", device)
+        self.tdev = tensor_device or torch.device("cpu")
+        self.send = torch.zeros((self.slots, self.width), dtype=torch.float64, device=self.tdev)
+        self.recv = torch.zeros((world * self.slots, self.width), dtype=torch.float64, device=self.tdev) if world > 1 else None
+        self.last_ms = {}
+
+    def close(self):
+        if self.batch is not None:
+            self.batch.close()
+            self.batch = None
+
+    def _solve_local(self, resident: bool):
+        """fills self.send; returns the local status arrays"""
+        import torch
+        n = len(self.mine)
+        trailer = np.zeros((self.slots, N_EXTRA))
+        if n == 0:
+            return trailer
+        if self.solve_fn is not None:
+            r = self.solve_fn([self.problems[i] for i in self.mine])
+            blk = np.zeros((self.slots, self.fo, self.stride))
+            f = np.asarray(r["final"])
+            blk[:n, :f.shape[1], :f.shape[2]] = f
+            self.send[:, :self.fo * self.stride] = torch.from_numpy(blk.reshape(self.slots, -1)).to(self.tdev)
+            frames, success, sstat, siter = r["frames"], r["success"], r["stage_status"], r["stage_iters"]
+        else:
+            b = self.batch
+            if resident:
+                b.reset()
+            B = b.B
+            sstat, siter, success = np.zeros((6, B), np.int32), np.zeros((6, B), np.int32), np.zeros((B, 2), np.int32)
+            b._chk(b.L.chd_phys_solve(b.h, None, None, success.ctypes.data, sstat.ctypes.data, siter.ctypes.data))
+            # final iterate sampled on the device straight into the send buffer (no host round trip)
+            fo_l, st_l = b.dims["frames_out_max"], 6 + 7 * b.n_ee_max
+            if fo_l == self.fo and st_l == self.stride:
+                view = self.send[:n, :self.fo * self.stride]
+                if view.is_contiguous():
+                    b._chk(b.L.chd_phys_sample_device(b.h, view.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                else:
+                    tmp = torch.zeros((n, self.fo * self.stride), dtype=torch.float64, device=self.tdev)
+                    b._chk(b.L.chd_phys_sample_device(b.h, tmp.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                    self.send[:n, :self.fo * self.stride] = tmp
+            else:   # ragged shards: local frame / stride padding differs from the global one
+                tmp = torch.zeros((n, fo_l, st_l), dtype=torch.float64, device=self.tdev)
+                b._chk(b.L.chd_phys_sample_device(b.h, tmp.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                blk = torch.zeros((n, self.fo, self.stride), dtype=torch.float64, device=self.tdev)
+                blk[:, :fo_l, :st_l] = tmp
+                self.send[:n, :self.fo * self.stride] = blk.reshape(n, -1)
+            frames = np.array([frames_out(self.problems[i]) for i in self.mine], np.int32)
+        trailer[:n, 0] = frames
+        trailer[:n, 1:3] = np.asarray(success).reshape(n, 2)
+        trailer[:n, 3:9] = np.asarray(sstat).T
+        trailer[:n, 9:15] = np.asarray(siter).T
+        self.send[:, self.fo * self.stride:] = torch.from_numpy(trailer).to(self.tdev)
+        return trailer
+
+    def solve(self, resident: bool = False) -> dict:
+        """Solves the shard (resident=True: device-side reset of an already uploaded batch) and gathers.  Every rank
+        returns the full result in the original sequence order."""
+        import time
+        import torch
+        import torch.distributed as dist
+        t0 = time.perf_counter()
+        self._solve_local(resident)
+        if self.tdev.type == "cuda":
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.recv.view(-1), self.send.view(-1), group=self.group)
+            if self.tdev.type == "cuda":
+                torch.cuda.synchronize()
+            g = self.recv
+        else:
+            g = self.send
+        t2 = time.perf_counter()
+        self.last_ms = {"solve_ms": 1e3 * (t1 - t0), "gather_ms": 1e3 * (t2 - t1)}
+        g = g.cpu().numpy()
+        full = unshard(g, self.shards, self.slots)
+        N = len(self.problems)
+        tr = full[:, self.fo * self.stride:]
+        return dict(samples=full[:, :self.fo * self.stride].reshape(N, self.fo, self.stride), frames=tr[:, 0].astype(np.int32),
+                    success=tr[:, 1:3].astype(np.int32), stage_status=tr[:, 3:9].astype(np.int32).T,
+                    stage_iters=tr[:, 9:15].astype(np.int32).T, d2h_bytes=int(g.nbytes))
+
+
+def solve_sharded(problems, weights=(0.4, 1.7, 0.3, 0.1, 0.1), device: int = 0, rank: int = 0, world: int = 1, group=None,
+                  solve_fn=None, tensor_device=None) -> dict:
+    """shard -> solve -> one gather -> unshard for a list of `PhysProblem`s (see ShardedSolver)."""
+    s = ShardedSolver(problems, weights, device, rank, world, group, solve_fn, tensor_device)
+    try:
+        return s.solve()
+    finally:
+        s.close()

@@ -50,7 +50,7 @@ EXPORTS = ["chd_version", "chd_phys_batch_create", "chd_phys_batch_destroy", "ch
            "chd_phys_get_x", "chd_phys_set_x", "chd_phys_eval", "chd_phys_get_layout", "chd_phys_solve_stage",
            "chd_phys_solve", "chd_phys_sample", "chd_phys_sample_device", "chd_phys_launch_count",
            "chd_phys_kernel_times", "chd_phys_set_timing", "chd_phys_h2d_bytes", "chd_phys_reset", "chd_measure_fp64_peak", "chd_phys_get_slot_index", "chd_phys_get_ent_col",
-           "chd_phys_get_duals", "chd_phys_stage_stats"]
+           "chd_phys_get_duals", "chd_phys_stage_stats", "chd_phys_get_sizes_fixed"]
 
 
 def measure_fp64_peak():
@@ -101,6 +101,7 @@ def load_lib():
         L.chd_phys_get_ent_col.argtypes = [vp, vp]
         L.chd_phys_get_duals.argtypes = [vp] * 7
         L.chd_phys_stage_stats.argtypes = [vp, vp]
+        L.chd_phys_get_sizes_fixed.argtypes = [vp, vp]
         L.chd_phys_get_slot_index.argtypes = [vp] * 4
         _LIB = L
     return _LIB
@@ -196,6 +197,12 @@ class PhysBatch:
                    row_kkt=np.zeros((B, d["m_max"]), np.int32))
         self._chk(self.L.chd_phys_get_layout(self.h, *[_ptr(out[k]) for k in ("ent_ptr", "ent_col", "row_lo", "row_hi",
                                                                               "row_set", "var_kkt", "row_kkt")]))
+        return out
+
+    def sizes_fixed(self) -> np.ndarray:
+        """(B, 3): border unknowns / half bandwidth of the fixed-duration stages, number of phase-duration variables."""
+        out = np.zeros((self.B, 3), np.int32)
+        self._chk(self.L.chd_phys_get_sizes_fixed(self.h, _ptr(out)))
         return out
 
     def ent_col(self) -> np.ndarray:

@@ -67,6 +67,10 @@ int chd_phys_get_dims(const chd_phys_batch* b, chd_phys_dims* dims);
 /* Per-sequence sizes: n (variables: node values, then the P-1 free phase durations of every foot), m (master rows),
  * nslots, Na, nb (border unknowns incl. the durations), w -- six int32 per sequence [host]. */
 int chd_phys_get_sizes(const chd_phys_batch* b, int32_t* sizes6);
+/* What the fixed-duration stages (all but stage 3) work with: border unknowns without the switch times, half bandwidth
+ * of the static pattern, and the number of phase-duration variables (0: stage 3 not available) -- three int32 per
+ * sequence [host]. */
+int chd_phys_get_sizes_fixed(const chd_phys_batch* b, int32_t* sizes3);
 
 /* Current iterate x: batch x n_max doubles.  [host] copies (synchronous). */
 int chd_phys_get_x(const chd_phys_batch* b, double* x_host);

@@ -47,6 +47,8 @@ int chdo_lag_hessian(void* h, const double* y, int* ri, int* ci, double* vals);
 void chdo_row_times(void* h, double* t);
 void chdo_var_times(void* h, double* t0, double* t1);
 int chdo_dur_blocks(void* h, int* off, int* cnt);
+void chdo_var_set_sizes(void* h, int* out);
+int chdo_n_ee(void* h);
 void chdo_init_durations(void* h, double* d);   // the free durations (first P-1 of every foot) of the input contact schedule
 }
 
@@ -427,6 +429,16 @@ struct Solver {
     const double nl_ke = dur_vars.empty() ? 0.0 : (getenv("CHD_NL_KE") ? atof(getenv("CHD_NL_KE")) : 1.0);   // stage 3 only (CHD_NL_GUARD in chd_dev.h)
     const double nl_fl = getenv("CHD_NL_FL") ? atof(getenv("CHD_NL_FL")) : 1e-4;
     double theta_ref = 0.0;
+    const double du_unobs = getenv("CHD_DU") ? atof(getenv("CHD_DU")) : 1e-4;   // CHD_DW_UNOBS of the product (csrc/chd_dev.h)
+    int mot_lo = 0, mot_hi = 0;
+    {
+      const int ne = chdo_n_ee(h);
+      std::vector<int> szs(2 + 3 * ne);
+      chdo_var_set_sizes(h, szs.data());
+      mot_lo = szs[0] + szs[1];
+      mot_hi = mot_lo;
+      for (int e = 0; e < ne; ++e) mot_hi += szs[2 + e];
+    }
     const double tau_trust = getenv("CHD_TAU_TRUST") ? atof(getenv("CHD_TAU_TRUST")) : 0.04;
     std::vector<double> x_init_dur(dur_vars.size());
     if (!dur_vars.empty()) chdo_init_durations(h, x_init_dur.data());
@@ -511,6 +523,16 @@ struct Solver {
       for (size_t k = 0; k < W1.v.size(); ++k) {
         int a = vk[W1.r[k]], b = vk[W1.c[k]];
         if (a >= 0 && b >= 0 && a >= b) K.add(a, b, sf * W1.v[k]);
+      }
+      if (du_unobs > 0.0) {
+        // foot-motion node values no cost sample sees (polynomials shorter than a frame): without curvature of their
+        // own the Newton step uses them as free slack and they drift by orders of magnitude; they get a fixed
+        // Levenberg-Marquardt weight instead of the adaptive one (what L-BFGS's initial scaling does for IPOPT)
+        std::vector<char> seen(n, 0);
+        for (size_t k = 0; k < W1.v.size(); ++k)
+          if (W1.r[k] == W1.c[k] && sf * W1.v[k] > 1e-14) seen[W1.r[k]] = 1;   // CHD_UNOBS_EPS
+        for (int i = mot_lo; i < mot_hi; ++i)
+          if (vk[i] >= 0 && !seen[i]) K.add(vk[i], vk[i], du_unobs);
       }
       for (size_t k = 0; k < W2.v.size(); ++k) {
         int a = vk[W2.r[k]], b = vk[W2.c[k]];
@@ -613,6 +635,7 @@ struct Solver {
           }
         }
         const double phit = sf * ft + bar;
+        if (verbose > 1) printf("        trial %d alpha %.6e theta_t %.6e phi_t %.9e\n", ls, alpha, theta_t, phit);
         bool okp = std::isfinite(phit) && std::isfinite(theta_t) && theta_t <= theta_max;
         // nonlinearity guard: the linearised constraints predict theta(alpha) = (1 - alpha) theta; the trial point is
         // refused while the second-order error exceeds nl_ke x the predicted decrease (or a small absolute level)

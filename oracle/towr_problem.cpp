@@ -1020,6 +1020,7 @@ int chdo_dur_blocks(void* h, int* off, int* cnt) {
   }
   return k;
 }
+int chdo_n_ee(void* h) { return ((Problem*)h)->n_ee; }
 void chdo_init_durations(void* h, double* d) {
   Problem* P = (Problem*)h;
   int k = 0;

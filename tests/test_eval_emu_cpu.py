@@ -112,3 +112,57 @@ def test_eval_source_matches_oracle(chd, n_ee, seed, stage):
     compare(chd, p, stage, rng, perturb_dur=False)
     if stage == "3":
         compare(chd, p, stage, rng, perturb_dur=True)     # polynomial boundaries moved: run-time columns
+
+
+def _fd_check(chd, p, seed):
+    """Central differences of the product's own g(x) / cost(x) with respect to every switch time tau_k (moving
+    tau_k by h changes d_k by +h and d_{k+1} by -h) against its analytic switch-time columns and gradient: an anchor
+    that does not involve the oracle."""
+    rng = np.random.default_rng(seed)
+    e0 = emu_eval(chd, p, 4)
+    n, nd = e0["n"], e0["n_dur"]
+    nn = n - nd
+    b = chd.phys.PhysBatch([p], host_only=True)
+    x = b.get_x()[0, :n].copy()
+    x[:nn] += rng.normal(0, 0.02, nn)
+    x[nn:] += rng.uniform(-0.01, 0.01, nd)
+    e = emu_eval(chd, p, 4, x, dyn=1)
+    h = 1e-6
+    cnts = [len(d) - 1 for d in p.ee_durations]
+    off = nn
+    worst = 0.0
+    for c in cnts:
+        for k in range(c):
+            xp, xm = x.copy(), x.copy()
+            xp[off + k] += h
+            xm[off + k] -= h
+            if k + 1 < c:
+                xp[off + k + 1] -= h
+                xm[off + k + 1] += h
+            ep, em = emu_eval(chd, p, 4, xp, dyn=1), emu_eval(chd, p, 4, xm, dyn=1)
+            col_fd = (ep["g"] - em["g"]) / (2 * h)
+            col = np.zeros(e["m"])
+            for r in range(e["m"]):
+                for q in range(e["ent_ptr"][r], e["ent_ptr"][r + 1]):
+                    if e["ent_col"][q] == off + k:
+                        col[r] += e["Jv"][q]
+            scale = max(1.0, np.abs(col_fd).max())
+            worst = max(worst, np.abs(col - col_fd).max() / scale)
+            g_fd = (ep["cost"][0] - em["cost"][0]) / (2 * h)
+            assert abs(g_fd - e["grad"][off + k]) <= 1e-5 * max(1.0, abs(g_fd)), (k, g_fd, e["grad"][off + k])
+        off += c
+    assert worst <= 1e-5, worst
+
+
+def test_switch_time_columns_finite_differences(chd):
+    _fd_check(chd, chd.synth.make_problem(3, n_frames=60, n_ee=2), 0)
+
+
+def test_switch_time_columns_finite_differences_random_points(chd):
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=4, deadline=None)
+    @given(st.integers(min_value=0, max_value=10_000))
+    def run(seed):
+        _fd_check(chd, chd.synth.make_problem(seed % 7, n_frames=40, n_ee=2 if seed % 2 else 4), seed)
+    run()

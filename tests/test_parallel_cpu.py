@@ -51,3 +51,55 @@ def test_shard_by_work_balanced(chd):
     assert sorted(s[0] + s[1]) == list(range(8))
     assert abs(sum(work[i] for i in s[0]) - sum(work[i] for i in s[1])) <= 2
     assert chd.parallel.shard_by_work([5, 5, 5], 4)[3] == []
+
+
+def _oracle_solve_fn(problems):
+    """stand-in for the CUDA solve of a shard in the CPU test: the oracle solves the same NLPs (test infrastructure)"""
+    from oracle.phys import OracleProblem
+    ids = {"1.1": 0, "1.2": 1, "2.1": 2, "2.2": 3, "3": 4, "4": 5}
+    finals, frames, succ = [], [], []
+    sstat, siter = np.full((6, len(problems)), -9, np.int32), np.zeros((6, len(problems)), np.int32)
+    for i, p in enumerate(problems):
+        r = OracleProblem(p).solve()
+        finals.append(r["durations"]), frames.append(len(r["durations"])), succ.append(r["success"])
+        for k, s in zip(r["stage_ids"], r["stages"]):
+            sstat[ids[k], i], siter[ids[k], i] = s["status"], s["iters"]
+    fo = max(frames)
+    blk = np.zeros((len(problems), fo, finals[0].shape[1]))
+    for i, f in enumerate(finals):
+        blk[i, :len(f)] = f
+    return dict(final=blk, frames=np.array(frames), success=np.array(succ, np.int32), stage_status=sstat, stage_iters=siter)
+
+
+def _worker_solve(rank, world, port, tmp):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    import chd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ps = [chd.synth.make_problem(s, n_frames=40 + 4 * s, n_ee=2) for s in range(3)]     # ragged lengths
+    out = chd.parallel.solve_sharded(ps, rank=rank, world=world, solve_fn=_oracle_solve_fn)
+    np.savez(os.path.join(tmp, "rank%d.npz" % rank), **{k: v for k, v in out.items() if k != "d2h_bytes"})
+    dist.destroy_process_group()
+
+
+def test_solve_sharded_gloo(tmp_path, chd):
+    """chd.parallel.solve_sharded (the path bench.py and scripts/phys_optim.py use on N > 1 GPUs) with world size 2 on
+    gloo: both ranks end up with every sequence's solved trajectory and status, in the original order."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_solve, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(str(tmp_path / "rank0.npz")), np.load(str(tmp_path / "rank1.npz"))
+    for k in r0.files:
+        np.testing.assert_array_equal(r0[k], r1[k])
+    ps = [chd.synth.make_problem(s, n_frames=40 + 4 * s, n_ee=2) for s in range(3)]
+    ref = _oracle_solve_fn(ps)
+    for i in range(3):
+        nf = ref["frames"][i]
+        assert r0["frames"][i] == nf == chd.parallel.frames_out(ps[i])
+        np.testing.assert_array_equal(r0["samples"][i, :nf], ref["final"][i, :nf])
+    np.testing.assert_array_equal(r0["stage_status"], ref["stage_status"])
+    np.testing.assert_array_equal(r0["stage_iters"], ref["stage_iters"])
+    assert (r0["success"] == 1).all()
