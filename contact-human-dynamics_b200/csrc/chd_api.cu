@@ -21,6 +21,8 @@ __global__ void chd_k_asm(ChdDev D);
 __global__ void chd_k_fp64_peak(int mode, int iters, double* sink);
 __global__ void chd_k_hess_base(ChdDev D);
 __global__ void chd_k_hess_dur(ChdDev D);
+__global__ void chd_k_hess_zero(ChdDev D);
+__global__ void chd_k_hess_fin(ChdDev D, int mode);
 __global__ void chd_k_tables(ChdDev D);
 __global__ void chd_k_clear_dyn(ChdDev D);
 __global__ void chd_k_linesearch(ChdDev D);
@@ -157,7 +159,10 @@ int run_schedule(chd_phys_batch* b) {
     }
     {
       Timer t(b, KT_INIT);
-      chd_k_hess_base<<<B, CHD_THREADS, 0, b->stream>>>(b->D);
+      chd_k_hess_zero<<<dim3(8, B), 256, 0, b->stream>>>(b->D);
+      chd_k_hess_base<<<dim3(8, B), CHD_THREADS, 0, b->stream>>>(b->D);
+      chd_k_hess_fin<<<B, 128, 0, b->stream>>>(b->D, 0);
+      b->launches += 2;
     }
     if (it > 0) {
       CHD_CUDA(cudaStreamWaitEvent(b->stream, b->ev_copy, 0));   // Kwork refreshed by the side stream
@@ -169,14 +174,12 @@ int run_schedule(chd_phys_batch* b) {
       if (b->D.win_smem) chd_k_kkt<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);
       else chd_k_kkt_gwin<<<B, CHD_KKT_THREADS, b->smem_kkt, b->stream>>>(b->D);
     }
-    // Kwork <- Kbase for the next iteration, overlapped with the line search / evaluation kernels.  With stage 3 in the
-    // schedule the cost Hessian (Kbase) of the sequences in that stage is rebuilt from the accepted iterate first.
-    if (!b->sched_has_dur) {
-      CHD_CUDA(cudaEventRecord(b->ev_kkt, b->stream));
-      CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_kkt, 0));
-      chd_k_kcopy<<<dim3(b->kcopy_blocks, B), 256, 0, b->copy_stream>>>(b->D);
-      b->launches++;
-    }
+    // Kwork <- Kbase for the next iteration, overlapped with the line search / evaluation kernels (sequences in stage 3
+    // are skipped: their cost Hessian moves with the durations and is rebuilt into Kwork after the line search)
+    CHD_CUDA(cudaEventRecord(b->ev_kkt, b->stream));
+    CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_kkt, 0));
+    chd_k_kcopy<<<dim3(b->kcopy_blocks, B), 256, 0, b->copy_stream>>>(b->D);
+    b->launches++;
     {
       Timer t(b, KT_LS);
       chd_k_linesearch<<<B, CHD_THREADS, b->smem_ls, b->stream>>>(b->D);
@@ -185,8 +188,8 @@ int run_schedule(chd_phys_batch* b) {
     CHD_CUDA(cudaEventRecord(b->ev_ls, b->stream));
     CHD_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_ls, 0));
     if (b->sched_has_dur) {
-      chd_k_hess_dur<<<B, CHD_THREADS, 0, b->copy_stream>>>(b->D);
-      chd_k_kcopy<<<dim3(b->kcopy_blocks, B), 256, 0, b->copy_stream>>>(b->D);
+      chd_k_hess_dur<<<dim3(8, B), CHD_THREADS, 0, b->copy_stream>>>(b->D);
+      chd_k_hess_fin<<<B, 128, 0, b->copy_stream>>>(b->D, 1);
       b->launches += 2;
     }
     chd_k_curv<<<dim3(8, B), 256, 0, b->copy_stream>>>(b->D);
@@ -314,7 +317,7 @@ static int batch_create_impl(const chd_phys_problem* problems, int32_t batch, co
 #undef UP
   const size_t B = hb.B, nm = B * hb.n_max, mm = B * hb.m_max;
 #define AL(field, cnt) if ((rc = dev_alloc(b, (cnt), &D.field))) return rc;
-  AL(x, nm) AL(xt, nm) AL(jty, nm) AL(dx, nm) AL(grad, nm) AL(g, mm) AL(gt, mm) AL(Jv, B * hb.slots_max) AL(rflag, mm)
+  AL(x, nm) AL(xt, nm) AL(jty, nm) AL(unobs, nm) AL(dx, nm) AL(grad, nm) AL(g, mm) AL(gt, mm) AL(Jv, B * hb.slots_max) AL(rflag, mm)
   AL(sc, mm) AL(dL, mm) AL(dU, mm) AL(s, mm) AL(y, mm) AL(zL, mm) AL(zU, mm) AL(ds, mm) AL(dy, mm) AL(dzL, mm) AL(dzU, mm)
   D.nbc_max = (hb.Na_max + 7) / 8;
   D.Q = (hb.w_max + 7) / 8 + 1;

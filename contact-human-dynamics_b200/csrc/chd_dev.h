@@ -74,6 +74,7 @@ struct ChdDev {
   double *g, *gt;                             // B x m_max   (unscaled constraint values at x / trial x)
   double* Jv;                                 // B x slots_max
   int* rflag;                                 // B x m_max
+  unsigned char* unobs;                       // B x n_max  foot-motion node values without cost curvature (chd_hess_build)
   double *sc, *dL, *dU, *s, *y, *zL, *zU, *ds, *dy, *dzL, *dzU;  // B x m_max
   double* cost;                               // B x 2 (current, trial)
   // ---- KKT ----

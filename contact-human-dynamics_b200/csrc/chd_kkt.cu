@@ -19,82 +19,84 @@
 #include "chd_eval.cuh"
 #include "chd_kkt_tiles.cuh"
 
-// Gauss-Newton Hessian of a least-squares cost sample: H += wgt * J^T J, where the sample residual (3 rows) is a
-// signed sum over (up to two) located polynomials of B(deriv) node values.  Every Jacobian column is a 3-vector:
+// Gauss-Newton Hessian of a least-squares cost sample by one warp: H += wgt * J^T J, where the sample residual (3 rows)
+// is a signed sum over (up to two) located polynomials of B(deriv) node values.  Every Jacobian column is a 3-vector:
 // wgt_q e_dim for a node slot, and -- stage 3, foot splines, positions -- the switch-time columns of chd_spl_tau.
-__device__ void chd_hess_sample(const ChdCtx& c, const ChdKT& K, const int* vk, int s, const ChdSpl* P, const double* sign, int np, int deriv,
-                                double wgt) {
-  int idx[28];
-  double cv[28][3];
-  int ne = 0;
-  for (int pa = 0; pa < np; ++pa) {
-    for (int qa = 0; qa < 12; ++qa) {
-      const int va = P[pa].var[qa];
-      const int ia = va >= 0 ? vk[va] : -1;
-      const double wa = sign[pa] * chd_slot_w(P[pa], deriv, qa);
-      if (ia < 0 || wa == 0.0) continue;
-      idx[ne] = ia;
-      cv[ne][0] = cv[ne][1] = cv[ne][2] = 0.0;
-      cv[ne][qa % 3] = wa;
-      ++ne;
-    }
-    if (c.opt_dur && s >= 2 && deriv == 0) {
-      ChdTau u;
-      chd_spl_tau(c, s, s - 2, P[pa], u);
-      if (u.va >= 0) {
-        idx[ne] = vk[u.va];
-        for (int d = 0; d < 3; ++d) cv[ne][d] = sign[pa] * u.da[d];
-        ++ne;
-      }
-      if (u.vb >= 0) {
-        idx[ne] = vk[u.vb];
-        for (int d = 0; d < 3; ++d) cv[ne][d] = sign[pa] * u.db[d];
-        ++ne;
+// Entry e = polynomial * 14 + slot (12 node slots, 2 switch-time slots); ws: 28 x 4 doubles of per-warp scratch
+// (kkt index or -1, column vector); the 28 x 28 pair loop is spread over the lanes.
+__device__ __forceinline__ void chd_hess_sample(const ChdCtx& c, const ChdKT& K, const int* vk, int s, const ChdSpl* P, const double* sign, int np,
+                                                int deriv, double wgt, int lane, double* ws) {
+  const bool tau = c.opt_dur && s >= 2 && deriv == 0;
+  if (lane < 28) {
+    const int pa = lane / 14, q = lane % 14;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    int ia = -1;
+    if (pa < np) {
+      if (q < 12) {
+        const int va = P[pa].var[q];
+        const double wa = sign[pa] * chd_slot_w(P[pa], deriv, q);
+        if (va >= 0 && wa != 0.0) {
+          ia = vk[va];
+          v0 = q % 3 == 0 ? wa : 0.0, v1 = q % 3 == 1 ? wa : 0.0, v2 = q % 3 == 2 ? wa : 0.0;
+        }
+      } else if (tau) {
+        ChdTau u;
+        chd_spl_tau(c, s, s - 2, P[pa], u);
+        const int var = q == 12 ? u.va : u.vb;
+        const double* dv = q == 12 ? u.da : u.db;
+        if (var >= 0) ia = vk[var], v0 = sign[pa] * dv[0], v1 = sign[pa] * dv[1], v2 = sign[pa] * dv[2];
       }
     }
+    ws[lane * 4 + 0] = (double)ia, ws[lane * 4 + 1] = v0, ws[lane * 4 + 2] = v1, ws[lane * 4 + 3] = v2;
   }
-  for (int a = 0; a < ne; ++a)
-    for (int bq = 0; bq < ne; ++bq) {
-      if (idx[a] < idx[bq]) continue;
-      const double v = cv[a][0] * cv[bq][0] + cv[a][1] * cv[bq][1] + cv[a][2] * cv[bq][2];
-      if (v != 0.0) chd_kadd(K, idx[a], idx[bq], wgt * v);
-    }
+  __syncwarp();
+  const int ne = np * 14;
+  for (int idx = lane; idx < ne * ne; idx += 32) {
+    const int a = idx / ne, bq = idx - a * ne;
+    const int ia = (int)ws[a * 4], ib = (int)ws[bq * 4];
+    if (ia < 0 || ib < 0 || ia < ib) continue;
+    const double v = ws[a * 4 + 1] * ws[bq * 4 + 1] + ws[a * 4 + 2] * ws[bq * 4 + 2] + ws[a * 4 + 3] * ws[bq * 4 + 3];
+    if (v != 0.0) chd_kadd(K, ia, ib, wgt * v);
+  }
+  __syncwarp();
 }
 
-// Kbase of sequence b: Gauss-Newton Hessian of the cost terms of data_cost.cpp / vel_smooth_cost.cpp /
-// duration_cost.cpp at the current x, scaled by the objective scaling.  Constant during a fixed-duration stage (the
-// costs are quadratic in the node values); in stage 3 the basis weights move with the durations and it is rebuilt
-// every iteration.
-__device__ void chd_hess_build(const ChdDev& D, int b, const ChdStageDev& sg) {
+// Cost part of the KKT matrix of sequence b: Gauss-Newton Hessian of the cost terms of data_cost.cpp /
+// vel_smooth_cost.cpp / duration_cost.cpp at the current x, scaled by the objective scaling, added into `base` (zeroed
+// before).  Constant during a fixed-duration stage (the costs are quadratic in the node values: Kbase, built when the
+// stage begins); in stage 3 the basis weights move with the durations and it is rebuilt into Kwork every iteration.
+// The samples are dealt to `nparts` CTAs (the reductions into L2 are the cost).
+__device__ void chd_hess_build(const ChdDev& D, int b, const ChdStageDev& sg, double* base, int part, int nparts) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const ChdSeq* h = D.seq + b;
   ChdKT K;
-  double* base = D.Kbase + (size_t)b * D.kstride;
   chd_kt_init(D, h, base, K);
   K.ovf = &D.ipm[b].band_ovf;
-  for (size_t i = tid; i < D.kstride; i += nt) base[i] = 0.0;
-  __syncthreads();
   const double sf = D.ipm[b].sf;
   const int* vk = D.var_kkt + (size_t)b * D.n_max;
-  for (int i = K.Na + tid; i < K.Np; i += nt) K.band[((size_t)(i >> 3) * K.Q) * 64 + (i & 7) * 9] = 1.0;  // identity padding of the band
   ChdCtx c;
   chd_make_ctx(D, b, D.x + (size_t)b * D.n_max, c);
   c.dyn = D.ipm[b].dyn;
   c.opt_dur = sg.opt_dur;
   const int n_ee = h->n_ee, nsp = 2 + n_ee, F = h->F, ns = h->n_smooth;
-  for (int it = tid; it < nsp * F; it += nt) {
+  // one warp per cost sample (the 28 x 28 pair loop of a sample is spread over its lanes)
+  __shared__ double s_hws[CHD_THREADS / 32][28 * 4];
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  for (int it = part * nwarp + warp; it < nsp * F; it += nparts * nwarp) {
     const int s = it / F, i = it % F, cls = s < 2 ? s : 2;
     ChdSpl P[2];
     double sgn[2] = {1.0, -1.0};
     chd_spl_at(c, s, c.t_data[i], P[1]);
-    if (sg.w_data[cls] != 0.0) chd_hess_sample(c, K, vk, s, P + 1, sgn, 1, 0, sf * sg.w_data[cls]);
+    if (sg.w_data[cls] != 0.0) chd_hess_sample(c, K, vk, s, P + 1, sgn, 1, 0, sf * sg.w_data[cls], lane, s_hws[warp]);
     if (i < ns && (sg.w_vel[cls] != 0.0 || sg.w_acc[cls] != 0.0)) {
       chd_spl_at(c, s, c.t_data[i] + h->dt, P[0]);
-      if (sg.w_vel[cls] != 0.0) chd_hess_sample(c, K, vk, s, P, sgn, 2, 0, sf * sg.w_vel[cls]);
-      if (sg.w_acc[cls] != 0.0) chd_hess_sample(c, K, vk, s, P, sgn, 2, 1, sf * sg.w_acc[cls]);
+      if (sg.w_vel[cls] != 0.0) chd_hess_sample(c, K, vk, s, P, sgn, 2, 0, sf * sg.w_vel[cls], lane, s_hws[warp]);
+      if (sg.w_acc[cls] != 0.0) chd_hess_sample(c, K, vk, s, P, sgn, 2, 1, sf * sg.w_acc[cls], lane, s_hws[warp]);
     }
   }
-  if (sg.opt_dur && sg.w_dur != 0.0) {   // duration_cost.cpp: w I in the durations = w D^T D in the switch times
+  if (part == 0)
+    for (int i = K.Na + tid; i < K.Np; i += nt) K.band[((size_t)(i >> 3) * K.Q) * 64 + (i & 7) * 9] = 1.0;  // identity padding of the band
+  if (part == 0 && sg.opt_dur && sg.w_dur != 0.0) {   // duration_cost.cpp: w I in the durations = w D^T D in the switch times
     for (int ee = 0; ee < n_ee; ++ee)
       for (int k = tid; k < h->n_phases[ee] - 1; k += nt) {
         const int i = vk[h->dur_xoff[ee] + k];
@@ -107,22 +109,66 @@ __device__ void chd_hess_build(const ChdDev& D, int b, const ChdStageDev& sg) {
       }
   }
 }
-
-__global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D) {
-  const int b = blockIdx.x;
-  if (D.ipm[b].phase != CHD_PH_BEGIN) return;
-  chd_hess_build(D, b, D.stages[D.ipm[b].stage]);
-  __syncthreads();
-  if (threadIdx.x == 0) D.ipm[b].phase = CHD_PH_RUN;
+// zero fill of one tile-format matrix, slice `part` of `nparts` (the identity padding of the band is written by
+// chd_hess_build, i.e. by a later kernel: the padding entries lie in some other CTA's slice)
+__device__ void chd_hess_clear(const ChdDev& D, int b, double* base, int part, int nparts) {
+  const size_t cnt2 = D.kstride / 2, per = (cnt2 + nparts - 1) / nparts;
+  const size_t lo = (size_t)part * per, hi = lo + per < cnt2 ? lo + per : cnt2;
+  double2* dst = reinterpret_cast<double2*>(base);
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = make_double2(0.0, 0.0);
 }
-// stage 3, every iteration after the line search (side stream, before chd_k_kcopy)
+
+// stage begin, grid (G, B): Kbase <- 0, then the cost Hessian, then (one CTA per sequence) the flags + BEGIN -> RUN
+__global__ void __launch_bounds__(256) chd_k_hess_zero(ChdDev D) {
+  const int b = blockIdx.y;
+  if (D.ipm[b].phase != CHD_PH_BEGIN) return;
+  chd_hess_clear(D, b, D.Kbase + (size_t)b * D.kstride, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_base(ChdDev D) {
+  const int b = blockIdx.y;
+  if (D.ipm[b].phase != CHD_PH_BEGIN) return;
+  chd_hess_build(D, b, D.stages[D.ipm[b].stage], D.Kbase + (size_t)b * D.kstride, blockIdx.x, gridDim.x);
+}
+// stage 3, every iteration after the line search (side stream, grid (G, B)): the cost Hessian at the accepted iterate
+// goes straight into Kwork, which chd_k_kcopy has zeroed for the sequences of that stage
 __global__ void __launch_bounds__(CHD_THREADS) chd_k_hess_dur(ChdDev D) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const ChdIpm& I = D.ipm[b];
   if (I.phase != CHD_PH_RUN || !I.kw_req) return;
   const ChdStageDev sg = D.stages[I.stage];
   if (!sg.opt_dur) return;
-  chd_hess_build(D, b, sg);
+  chd_hess_build(D, b, sg, D.Kwork + (size_t)b * D.kstride, blockIdx.x, gridDim.x);
+}
+// after the cost Hessian is complete: foot-motion node values that no cost sample sees (zero diagonal) are flagged for
+// chd_assemble's fixed regularisation.  mode 0 (main stream): sequences at the beginning of a stage (Kbase), which then
+// start running; mode 1 (side stream): sequences iterating in stage 3 (Kwork, before the curvature terms are added)
+__global__ void __launch_bounds__(128) chd_k_hess_fin(ChdDev D, int mode) {
+  const int b = blockIdx.x;
+  ChdIpm& I = D.ipm[b];
+  const double* base;
+  if (mode == 0) {
+    if (I.phase != CHD_PH_BEGIN) return;
+    base = D.Kbase + (size_t)b * D.kstride;
+  } else {
+    if (I.phase != CHD_PH_RUN || !I.kw_req || !D.stages[I.stage].opt_dur) return;
+    base = D.Kwork + (size_t)b * D.kstride;
+  }
+  const ChdSeq* h = D.seq + b;
+  const int* vk = D.var_kkt + (size_t)b * D.n_max;
+  const double* corn = base + (size_t)D.nbc_max * D.Q * 64 + (size_t)D.nbc_max * D.nbt * 64;
+  unsigned char* un = D.unobs + (size_t)b * D.n_max;
+  const int mot_lo = h->sp_xoff[2], mot_hi = h->sp_xoff[2 + h->n_ee], Na = h->Na;
+  for (int i = mot_lo + threadIdx.x; i < mot_hi; i += blockDim.x) {
+    const int k = vk[i];
+    unsigned char f = 0;
+    if (k >= 0) {
+      const double hd = k < Na ? base[((size_t)(k >> 3) * D.Q) * 64 + (k & 7) * 9] : corn[(size_t)(k - Na) * 8 * D.nbt + (k - Na)];
+      f = hd <= CHD_UNOBS_EPS;
+    }
+    un[i] = f;
+  }
+  __syncthreads();
+  if (mode == 0 && threadIdx.x == 0) I.phase = CHD_PH_RUN;
 }
 
 // y^+ * Jd^T Jd of the squared-distance rows (leg length, toe-heel distance) of sequence b added into K: one warp
@@ -252,16 +298,11 @@ __device__ __forceinline__ void chd_assemble(const ChdDev& D, int b, const ChdKT
   // the Newton step uses them as free slack and they drift by orders of magnitude, which stage 3 (where the sample
   // times sweep over those polynomials) cannot digest.  They get a fixed Levenberg-Marquardt weight on top of the
   // adaptive one -- what the initial scaling of IPOPT's L-BFGS matrix does for the reference.
-  const double* kb = D.Kbase + (size_t)b * D.kstride;
-  const double* kb_corn = kb + (size_t)D.nbc_max * D.Q * 64 + (size_t)D.nbc_max * D.nbt * 64;
-  const int mot_lo = h->sp_xoff[2], mot_hi = h->sp_xoff[2 + h->n_ee];
+  const unsigned char* unobs = D.unobs + vo;
   for (int i = t0; i < n; i += tstep) {
     const int k = vk[i];
     if (k < 0) continue;
-    if (do_mat && i >= mot_lo && i < mot_hi) {
-      const double hd = k < Na ? kb[((size_t)(k >> 3) * K.Q) * 64 + (k & 7) * 9] : kb_corn[(size_t)(k - Na) * K.nbp8 + (k - Na)];
-      if (hd <= CHD_UNOBS_EPS) mat_add(k, k, CHD_DW_UNOBS);
-    }
+    if (do_mat && unobs[i]) mat_add(k, k, CHD_DW_UNOBS);
     mat_add(k, k, delta_w);
     rhs_add(k, -sf * grad[i]);
     g_add(k, -sf * grad[i], 0.0);
@@ -368,7 +409,10 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   if (!sg.opt_dur) K.q = D.Qfix - 1;   // fixed-duration stages: the static pattern needs fewer band tiles than stage 3 may
   // (below, Q is the number of block rows of the elimination window of this stage, Qs the storage stride of a block column)
   const int n_act = sg.opt_dur ? n : n - h->n_dur;          // the durations (last n_dur entries of x) are unknowns in stage 3 only
-  const int Qs = K.Q, Q = sg.opt_dur ? K.Q : D.Qfix, nbt = K.nbt, nbp8 = K.nbp8, NBR = K.nbr, nbl = sg.opt_dur ? h->nb : h->nb_fix, nbc = K.nbc;
+  const int Qs = K.Q, Q = sg.opt_dur ? K.Q : D.Qfix, nbt = K.nbt, nbp8 = K.nbp8, nbl = sg.opt_dur ? h->nb : h->nb_fix, nbc = K.nbc;
+  // the right-hand side rides along as border row NBR, directly behind the border unknowns of this stage; nbt_s = border
+  // tiles in use (the switch-time columns of stage 3 are all zero in the fixed-duration stages: not even looked at)
+  const int NBR = nbl, nbt_s = (nbl + 1 + 7) >> 3;
   // WS: everything in shared memory.  !WS (long horizons / very wide bands): only the reduction buffer, the
   // corner and the panel buffers stay in shared memory; the per-unknown vectors and the window live in a global
   // (L2 resident) scratch area  vecn | xs | xs2 | win | bwin.
@@ -567,7 +611,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   __shared__ unsigned short s_pairs[3000];
   __shared__ unsigned char s_cmp[CHD_KKT_THREADS / 32][64];   // per warp: rank -> id of the non-zero panel groups
   __shared__ __align__(16) double s_winv[2][64];   // inverse of the current / next diagonal tile factor, fragment order
-  const int GB = K.q, Gm = K.q + nbt, npairs = Gm * (Gm + 1) / 2;
+  const int GB = K.q, Gm = K.q + nbt_s, npairs = Gm * (Gm + 1) / 2;
   for (int p = tid; p < npairs && p < 3000; p += nt) {
     int gi = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
     while (gi * (gi + 1) / 2 > p) --gi;
@@ -605,7 +649,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
       const double2 wf = *reinterpret_cast<const double2*>(wv + 2 * lane);
       const double d0 = dv[2 * k], d1 = dv[2 * k + 1];
       const int f0 = r * 8 + chd_frag_col(2 * k), f1 = r * 8 + chd_frag_col(2 * k + 1);
-      for (int g = warp; g < tq + nbt; g += nwarp) {
+      for (int g = warp; g < tq + nbt_s; g += nwarp) {
         const bool band_t = g < tq;
         const int pg = band_t ? g : GB + (g - tq);                   // group id inside the panel buffers
         const double* A = band_t ? (WS ? win + (size_t)tri(rs[g], kslot) * 64 : K.band + ((size_t)Kc * Qs + 1 + g) * 64) : Bk + (g - tq) * 64;
@@ -635,7 +679,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     if (WS && In < nbc) {
       // 16-byte chunks; warp 0 goes straight to the diagonal tile (dedicating two warps to the stream-in was measured
       // slower: 482 vs 470 ms of KKT time per benchmark step)
-      for (int idx = tid - 32; idx < Q * 32 + nbt * 32; idx += nt - 32) {
+      for (int idx = tid - 32; idx < Q * 32 + nbt_s * 32; idx += nt - 32) {
         if (idx < 0) break;
         const int tile = idx >> 5, off = (idx & 31) * 2;
         if (tile < Q) {
@@ -1047,6 +1091,11 @@ __global__ void __launch_bounds__(256) chd_k_kcopy(ChdDev D) {
   if (blockIdx.x == 0) {   // right-hand side accumulators of chd_k_asm
     const size_t go = (size_t)b * (D.Na_max + D.nb_max);
     for (int i = threadIdx.x; i < D.Na_max + D.nb_max; i += blockDim.x) D.rhs0[go + i] = 0.0, D.rhs1[go + i] = 0.0;
+  }
+  if (D.stages[D.ipm[b].stage].opt_dur && D.ipm[b].phase == CHD_PH_RUN) {
+    // stage 3: the cost Hessian moves with the durations; chd_k_hess_dur rebuilds it into a cleared Kwork after the line search
+    chd_hess_clear(D, b, D.Kwork + (size_t)b * D.kstride, blockIdx.x, gridDim.x);
+    return;
   }
   const size_t cnt2 = D.kstride / 2, per = (cnt2 + gridDim.x - 1) / gridDim.x;
   const size_t lo = (size_t)blockIdx.x * per, hi = lo + per < cnt2 ? lo + per : cnt2;
