@@ -211,3 +211,116 @@ def test_fp64_peak_probe(chd):
     dfma, dmma = chd.phys.measure_fp64_peak()
     assert 5e3 < dfma < 2e5 and 5e3 < dmma < 2e5
     assert 0.3 < dfma / dmma < 3.0
+
+
+def _oracle_full(seed_nee):
+    import chd as _chd
+    from oracle.phys import OracleProblem
+    seed, n_ee = seed_nee
+    r = OracleProblem(_chd.synth.make_problem(seed, n_ee=n_ee)).solve()
+    return seed, r["stage_ids"], [s["iters"] for s in r["stages"]], [s["status"] for s in r["stages"]], r["durations"]
+
+
+@pytest.mark.parametrize("n_ee,n_seq,min_same", [(2, 64, 0.9), (4, 16, 0.7)])
+def test_bench_batch_matches_oracle(chd, n_ee, n_seq, min_same):
+    """Every sequence of the benchmark batch (BASELINE configs[1]: 64 two-foot sequences; 16 four-foot ones) against the
+    CPU oracle, solved independently in a process pool: status of every stage equal for all sequences; iteration counts
+    of the fixed-duration stages equal for all, of stage 3 for at least 90 % of the two-foot and 70 % of the four-foot
+    sequences (measured: 64/64 resp. 12/16 -- the guarded line search of stage 3 flips on rounding along long, heavily
+    damped paths; both sides then still converge to the same tolerances); final trajectories compared wherever the
+    iteration counts agree."""
+    import multiprocessing as mp
+    import os
+    ps = [chd.synth.make_problem(s, n_ee=n_ee) for s in range(n_seq)]
+    b = chd.phys.PhysBatch(ps)
+    out = b.solve()
+    with mp.get_context("fork").Pool(min(n_seq, os.cpu_count() or 1)) as pool:
+        refs = pool.map(_oracle_full, [(s, n_ee) for s in range(n_seq)])
+    same3, fixed_ok = 0, 0
+    dpos, dfrc = [], []
+    for seed, ids, iters, status, final in refs:
+        gid = [GPU_STAGE_IDS[k] for k in ids]
+        g_it = [int(out["stage_iters"][s, seed]) for s in gid]
+        g_st = [int(out["stage_status"][s, seed]) for s in gid]
+        assert g_st == status, (seed, ids, g_st, status)
+        assert g_it[:4] == iters[:4], (seed, g_it, iters)
+        fixed_ok += 1
+        if g_it == iters:
+            same3 += 1
+            nf = out["frames"][seed]
+            got = out["samples"][2, seed, :nf]
+            dpos.append(np.abs(got[:, :6 + 3 * n_ee] - final[:, :6 + 3 * n_ee]).max())
+            dfrc.append(np.abs(got[:, 6 + 3 * n_ee:6 + 6 * n_ee] - final[:, 6 + 3 * n_ee:6 + 6 * n_ee]).max())
+            np.testing.assert_array_equal(got[:, 6 + 6 * n_ee:], final[:, 6 + 6 * n_ee:])
+    dpos, dfrc = np.array(dpos), np.array(dfrc)
+    print("max |pos diff| per sequence: median %.2e, 90%% %.2e, max %.2e; forces: median %.2e, max %.2e" % (
+        np.median(dpos), np.quantile(dpos, 0.9), dpos.max(), np.median(dfrc), dfrc.max()))
+    # rounding differences grow along long, heavily damped stage-3 paths (same iteration count, up to ~1e-3 m apart after a
+    # few hundred iterations: the termination tolerance of 1e-3 leaves that much room): most sequences agree to 1e-5 m,
+    # every one to 5e-3 m / 5 N
+    assert np.median(dpos) <= 1e-5 and dpos.max() <= 5e-3 and dfrc.max() <= 5.0
+    print("stage-3 iteration counts equal for %d / %d sequences" % (same3, n_seq))
+    assert same3 >= min_same * n_seq, same3
+
+
+def test_kkt_conditions_recomputed_independently(chd):
+    """KKT residuals of the GPU's final primal-dual point recomputed on the host with the ORACLE's NLP callbacks
+    (values, Jacobian, gradient: finite-difference verified in test_oracle_cpu.py) and numpy -- none of the solver's own
+    error measures is used.  IPOPT's termination test of phys_optim.cpp:578: scaled stationarity / feasibility /
+    complementarity <= tol = 1e-3, unscaled constraint violation <= constr_viol_tol = 1e-4."""
+    from oracle.phys import OracleProblem
+    ps = [chd.synth.make_problem(s, n_ee=2) for s in (0, 1, 2, 3)]
+    b = chd.phys.PhysBatch(ps)
+    out = b.solve()
+    x = b.get_x()
+    du = b.duals()
+    lay = b.layout()
+    for i, p in enumerate(ps):
+        assert out["stage_status"][4, i] == 0          # stage 3 converged: the point below is its final iterate
+        o = OracleProblem(p)
+        o.set_stage("3")
+        n = o.n
+        o.set_x(x[i, :n])
+        sl = chd.phys.master_row_slices(b, i, lay)
+        im, io = master_to_oracle_perm(sl, o)
+        assert len(io) == o.m
+        c, J, g = o.cons(), o.jac().tocsr(), o.grad()
+        cl, cu = o.con_bounds()
+        sc, sf = du["row_scale"][i], du["obj_scale"][i]
+        y, zL, zU, s = du["y"][i], du["zL"][i], du["zU"][i], du["s"][i]
+        # primal feasibility (unscaled), incl. the duration bounds d >= 0
+        nd = sum(len(d) - 1 for d in p.ee_durations)
+        viol = max(np.maximum(cl - c, c - cu).max(), (-x[i, n - nd:n]).max(), 0.0)
+        assert viol <= 1e-4, viol
+        # stationarity of the scaled problem  sf grad f + J^T (sc y) = 0  (+ the bound rows of the durations)
+        lam = np.zeros(o.m)
+        lam[io] = (sc * y)[im]
+        r = sf * g + J.T @ lam
+        rows_dp = np.concatenate([np.arange(a, e) for nm, a, e in sl if nm == "durpos"])
+        r[n - nd:n] += (sc * y)[rows_dp]
+        blocks = duration_blocks(p, n)
+        r_tau = to_tau(r, blocks)                                   # what the solver drives to zero (switch-time space)
+        free = lay["var_kkt"][i, :n] >= 0
+        rows_all = np.concatenate([im, rows_dp])
+        ineq = (lay["row_lo"][i, rows_all] != lay["row_hi"][i, rows_all])
+        z1 = np.abs(y[rows_all]).sum() + (zL[rows_all][ineq] + zU[rows_all][ineq]).sum()
+        nb = int(np.isfinite(np.where(lay["row_lo"][i, rows_all][ineq] > -1e19, 1.0, np.inf)).sum() +
+                 np.isfinite(np.where(lay["row_hi"][i, rows_all][ineq] < 1e19, 1.0, np.inf)).sum())
+        s_d = max(100.0, z1 / (len(rows_all) + nb)) / 100.0
+        assert np.abs(r_tau[free]).max() / s_d <= 1e-3, (np.abs(r_tau[free]).max(), s_d)
+        # slack consistency and complementarity of the inequality rows
+        cm = np.zeros(len(y))
+        cm[im] = c[io]
+        cm[rows_dp] = x[i, n - nd:n]
+        ri = rows_all[ineq]
+        assert np.abs(sc[ri] * cm[ri] - s[ri]).max() <= 1e-3
+        lo_s, hi_s = lay["row_lo"][i, ri] * sc[ri], lay["row_hi"][i, ri] * sc[ri]
+        relax = lambda v: 1e-8 * np.maximum(1.0, np.abs(v))
+        comp = []
+        hasl, hasu = lay["row_lo"][i, ri] > -1e19, lay["row_hi"][i, ri] < 1e19
+        comp.append(((s[ri] - (lo_s - relax(lo_s))) * zL[ri])[hasl])
+        comp.append((((hi_s + relax(hi_s)) - s[ri]) * zU[ri])[hasu])
+        comp = np.concatenate(comp)
+        s_c = max(100.0, (zL[ri][hasl].sum() + zU[ri][hasu].sum()) / max(len(comp), 1)) / 100.0
+        assert (comp >= 0).all() and comp.max() / s_c <= 1e-3, (comp.max(), s_c)
+        assert np.abs(-y[ri] - zL[ri] + zU[ri]).max() / s_d <= 1e-3
