@@ -38,7 +38,27 @@ def main(argv=None):
     print("Out Dir: %s\nInput Directory: %s\nnum frames: %s" % (args.out_dir, args.in_dir, args.nframes))
     print("Optim weights (%g, %g, %g, %g)\nDuration cost weight %g" % (args.w_com_lin, args.w_com_ang, args.w_ee, args.w_smooth, args.w_dur))
     problems = [chd.io_formats.read_phys_inputs(d, f, n_ee=args.n_ee) for d, f in zip(in_dirs, nframes)]
-    batch = chd.phys.PhysBatch(problems, weights=(args.w_com_lin, args.w_com_ang, args.w_ee, args.w_smooth, args.w_dur))
+    weights = (args.w_com_lin, args.w_com_ang, args.w_ee, args.w_smooth, args.w_dur)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        # torchrun: one process per GPU, sequences sharded by predicted work, one gather of the final trajectories;
+        # only the durations snapshot travels, so the sharded mode writes sol_out_durations.txt + success_log.txt
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        out = chd.parallel.solve_sharded(problems, weights=weights, device=local, rank=rank, world=world)
+        dist.destroy_process_group()
+        if rank == 0:
+            ne_max = max(p.n_ee for p in problems)
+            for i, (p, od) in enumerate(zip(problems, out_dirs)):
+                nf, n_ee = int(out["frames"][i]), p.n_ee
+                cols = list(range(6)) + [6 + 3 * e + d for e in range(n_ee) for d in range(3)] + \
+                    [6 + 3 * ne_max + 3 * e + d for e in range(n_ee) for d in range(3)] + [6 + 6 * ne_max + e for e in range(n_ee)]
+                chd.io_formats.write_solution(os.path.join(od, "sol_out_durations.txt"), p.dt, out["samples"][i, :nf][:, cols], n_ee)
+                chd.io_formats.write_success_log(os.path.join(od, "success_log.txt"), out["success"][i, 0], out["success"][i, 1])
+        return
+    batch = chd.phys.PhysBatch(problems, weights=weights)
     out = batch.solve()
     names = ["sol_out_no_dynamics.txt", "sol_out_dynamics.txt", "sol_out_durations.txt"]
     for i, (p, od) in enumerate(zip(problems, out_dirs)):
