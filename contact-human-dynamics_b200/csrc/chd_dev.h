@@ -108,6 +108,7 @@ struct ChdDev {
 #define CHD_BOUND_RELAX 1e-8
 #define CHD_DELTA_W0 1e-4
 #define CHD_DELTA_C 1e-8
+#define CHD_DW_POLISH 1.0   /* Levenberg-Marquardt weight of a feasibility-polish step (every test but the unscaled violation passes) */
 #define CHD_DW_MIN 1e-8
 #define CHD_DW_MAX 1e4
 #define CHD_DW_INC 4.0

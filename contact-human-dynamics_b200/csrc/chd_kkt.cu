@@ -543,7 +543,12 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   }
   if (done) return;
   const double tau = fmax(CHD_TAU_MIN, 1.0 - mu);
-  const double delta_w = I.delta_w;
+  // feasibility polish: every test but the unscaled constraint violation passes -> this step only restores feasibility
+  // (a large Levenberg-Marquardt weight makes it the least-norm Newton correction of the constraints; the adaptive
+  // weight itself is left alone)
+  const bool polish = E0 <= CHD_TOL && dual_u <= CHD_DUAL_INF_TOL && compl_u <= CHD_COMPL_INF_TOL && violu > CHD_CONSTR_VIOL_TOL &&
+                      I.delta_w < CHD_DW_POLISH;
+  const double delta_w = polish ? CHD_DW_POLISH : I.delta_w;
   CHD_PROF(0);
 
   // ---------------- B. assemble the KKT system ----------------
@@ -570,6 +575,11 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   // matrix entries do not depend on the barrier parameter: for sequences that continue in their stage they were
   // added by chd_k_asm (8 CTAs per sequence) before this kernel; the right-hand side (shared-memory atomics) is
   // always assembled here
+  if (pre_refreshed && polish) {   // chd_k_asm put the adaptive weight on the diagonal: top it up
+    const double extra = delta_w - I.delta_w;
+    for (int i = tid; i < n_act; i += nt)
+      if (vk[i] >= 0) chd_kadd(K, vk[i], vk[i], extra);
+  }
   if (pre_refreshed) {
     const double* r0 = D.rhs0 + (size_t)b * (D.Na_max + D.nb_max);
     const double* r1 = D.rhs1 + (size_t)b * (D.Na_max + D.nb_max);

@@ -429,6 +429,8 @@ struct Solver {
     const double nl_ke = dur_vars.empty() ? 0.0 : (getenv("CHD_NL_KE") ? atof(getenv("CHD_NL_KE")) : 1.0);   // stage 3 only (CHD_NL_GUARD in chd_dev.h)
     const double nl_fl = getenv("CHD_NL_FL") ? atof(getenv("CHD_NL_FL")) : 1e-4;
     double theta_ref = 0.0;
+    const double polish_dw = getenv("CHD_POLISH") ? atof(getenv("CHD_POLISH")) : 1.0;   // CHD_DW_POLISH of the product (csrc/chd_dev.h)
+    int n_polish = 0;
     const double du_unobs = getenv("CHD_DU") ? atof(getenv("CHD_DU")) : 1e-4;   // CHD_DW_UNOBS of the product (csrc/chd_dev.h)
     int mot_lo = 0, mot_hi = 0;
     {
@@ -507,6 +509,11 @@ struct Solver {
       if (getenv("CHD_MU_RESCUE") && E0 <= o.tol && violu <= o.constr_viol_tol && dual_u <= o.dual_inf_tol && compl_u > o.compl_inf_tol &&
           mu <= mu_min * 1.0000001)
         mu_min = std::max(mu_min / 5.0, 1e-9), mu = mu_min;
+      // feasibility polish: every test but the unscaled constraint violation passes -> this step only restores
+      // feasibility (a large Levenberg-Marquardt weight makes it the least-norm Newton correction of the constraints)
+      const bool polish = polish_dw > 0.0 && E0 <= o.tol && dual_u <= o.dual_inf_tol && compl_u <= o.compl_inf_tol && violu > o.constr_viol_tol;
+      const double delta_w_state = delta_w;
+      if (polish) delta_w = std::max(delta_w, polish_dw), n_polish++;
       const double tau = std::max(o.tau_min, 1.0 - mu);
       if (it == 0) theta_max = 1e4 * std::max(1.0, theta), theta_min = 1e-4 * std::max(1.0, theta), theta_ref = theta;
       if (mu != mu_filter) filt.clear(), mu_filter = mu;
@@ -576,6 +583,7 @@ struct Solver {
         continue;
       }
       if (!ok) {
+        if (polish) delta_w = delta_w_state;
         delta_w = std::min(std::max(delta_w * 100.0, 1e-4), o.dw_max * 10);
         ls_fail++;
         if (delta_w > o.dw_max) {
@@ -670,6 +678,7 @@ struct Solver {
         ls_fail++;
       }
       if (accepted && !ftype && (int)filt.size() < o.filt_max) filt.emplace_back((1 - o.gamma_theta) * theta, phi0 - o.gamma_phi * theta);
+      if (polish) delta_w = delta_w_state;
       {
         const int ls_f = rt0 > 0.0 ? ls - nl_rej : ls;   // trials refused by the filter itself
         const double dec3 = (!dur_vars.empty() && getenv("CHD_DW_DEC3")) ? atof(getenv("CHD_DW_DEC3")) : o.dw_dec;
