@@ -1,9 +1,9 @@
 """Host side of the foot-contact classifier path (reference: scripts/run_detect_contacts.py ->
 src/contact_learning/test.py --full-video --save-contacts --real-data).
 
-Keypoint loading and the dataset preprocessing are restated in numpy with the reference's operation order (they
-are fp64 on the host in the reference too); window construction, the MLP and the vote aggregation run in
-hand-written CUDA behind `chd_contact_*` (include/chd.h).  No CPU fallback for the network.
+Keypoint loading (JSON) happens on the host; the dataset preprocessing (padding, scaling, low-confidence
+interpolation, normalisation: real_video_dataset.py:132-163, openpose_dataset.py:49-121), window construction, the MLP
+and the vote aggregation run in hand-written CUDA behind `chd_contact_*` (include/chd.h).  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -38,57 +38,11 @@ def load_keypoint_dir(path: str) -> np.ndarray:
     return np.stack([load_keypoint_file(f) for f in files], axis=0)
 
 
-def interpolate_low_confidence(seq: np.ndarray, thresh: float = 0.2) -> np.ndarray:
-    """process_openpose_data (openpose_dataset.py:49-111) for one (F,J,3) sequence, in place on xy:
-    leading / trailing low-confidence runs copy the nearest valid frame, interior runs are linearly interpolated
-    with the reference's accumulating step."""
-    xy, conf = seq[:, :, :2], seq[:, :, 2]
-    F = seq.shape[0]
-    for j in range(seq.shape[1]):
-        t = 0
-        while t < F:
-            if conf[t, j] < thresh:
-                nxt = t + 1
-                while nxt < F and conf[nxt, j] < thresh:
-                    nxt += 1
-                init = t - 1
-                if t == 0 and nxt == F:
-                    pass
-                elif t == 0:
-                    xy[:nxt, j, :] = xy[nxt, j, :].reshape((1, 2))
-                elif nxt == F:
-                    xy[init:, j, :] = xy[init, j, :].reshape((1, 2))
-                else:
-                    step = 1.0 / (nxt - init)
-                    cur = step
-                    ct = t
-                    while ct < nxt:
-                        xy[ct, j, :] = (1.0 - cur) * xy[init, j, :] + cur * xy[nxt, j, :]
-                        ct += 1
-                        cur += step
-                t = nxt
-            else:
-                t += 1
-    return seq
-
-
-def preprocess_videos(raw: Sequence[np.ndarray], dimensions=(1920, 1080)):
-    """RealVideoDataset.__init__ (real_video_dataset.py:132-163): pad every video to the longest by repeating the
-    last frame, scale xy by 1280/width, interpolate low-confidence joints, divide xy by the training normalisation.
-    Returns (frames (V,Fmax,25,3) fp64, seq_lens (V,) int32)."""
-    seq_lens = np.array([r.shape[0] for r in raw], dtype=np.int32)
-    Fmax = int(seq_lens.max())
-    out = np.zeros((len(raw), Fmax, 25, 3))
-    scale = float(TRAIN_DIM[0]) / dimensions[0]
-    for i, r in enumerate(raw):
-        a = np.array(r, dtype=np.float64)
-        if a.shape[0] < Fmax:
-            a = np.concatenate([a, np.repeat(a[-1].reshape((1, 25, 3)), Fmax - a.shape[0], axis=0)], axis=0)
-        a[:, :, :2] *= scale
-        a = interpolate_low_confidence(a, 0.2)
-        a[:, :, :2] /= TRAIN_NORMALIZATION
-        out[i] = a
-    return out, seq_lens
+def concat_videos(raw: Sequence[np.ndarray]):
+    """list of (F_i,25,3) keypoint arrays -> (sum F, 25, 3) fp64 + (V+1,) int32 frame offsets (what chd_contact_* take)."""
+    offs = np.zeros(len(raw) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([r.shape[0] for r in raw])
+    return np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64) for r in raw], axis=0)), offs
 
 
 def pack_state_dict(sd: Dict[str, np.ndarray]):
@@ -117,6 +71,8 @@ class ContactNet:
         L.chd_contact_destroy.argtypes = [C.c_void_p]
         L.chd_contact_destroy.restype = None
         L.chd_contact_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.chd_contact_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.chd_contact_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.chd_contact_launch_count.argtypes = [C.c_void_p]
         L.chd_contact_launch_count.restype = C.c_int64
         w, b, bn = pack_state_dict(state_dict)
@@ -152,6 +108,32 @@ class ContactNet:
             raise RuntimeError("chd_contact_forward failed with code %d" % rc)
         return (labels, logits, float(mabs[0])) if want_logits else (labels, float(mabs[0]))
 
+    def preprocess(self, raw: Sequence[np.ndarray], dimensions=(1920, 1080)):
+        """RealVideoDataset.__init__ on the device (`chd_contact_preprocess`): list of raw (F_i,25,3) keypoints ->
+        (frames (V,Fmax,25,3) fp64, seq_lens (V,) int32), bit identical to the reference's numpy result."""
+        cat, offs = concat_videos(raw)
+        V, Fmax = len(raw), int(np.diff(offs).max())
+        frames = np.zeros((V, Fmax, 25, 3))
+        lens = np.zeros(V, dtype=np.int32)
+        rc = self.L.chd_contact_preprocess(self.h, cat.ctypes.data, offs.ctypes.data, V, int(dimensions[0]), frames.ctypes.data, lens.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("chd_contact_preprocess failed with code %d" % rc)
+        return frames, lens
+
+    def detect(self, raw: Sequence[np.ndarray], dimensions=(1920, 1080), cat=None, offs=None):
+        """raw keypoints -> list of (F_i,4) int64 foot-contact labels (`chd_contact_detect`: preprocessing, windows,
+        network, votes on the device; one upload, one download).  `cat` / `offs` may carry a pre-concatenated (e.g.
+        page-locked) buffer."""
+        if cat is None:
+            cat, offs = concat_videos(raw)
+        V = len(offs) - 1
+        lab = np.zeros((int(offs[-1]), 4), dtype=np.int64)
+        mabs = np.zeros(1, dtype=np.float32)
+        rc = self.L.chd_contact_detect(self.h, cat.ctypes.data, offs.ctypes.data, V, int(dimensions[0]), lab.ctypes.data, mabs.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("chd_contact_detect failed with code %d" % rc)
+        return [lab[offs[i]:offs[i + 1]] for i in range(V)], float(mabs[0])
+
     def launch_count(self) -> int:
         return int(self.L.chd_contact_launch_count(self.h))
 
@@ -161,13 +143,12 @@ def detect_contacts(data_root: str, out_root: str, state_dict, dimensions=(1920,
     `openpose_result/` writes O/contact_results/<video>/foot_contacts.npy (int64, F x 4), test.py:143-152."""
     vids = sorted(d for d in os.listdir(data_root) if os.path.isdir(os.path.join(data_root, d)) and d[0] != ".")
     raw = [load_keypoint_dir(os.path.join(data_root, v, "openpose_result")) for v in vids]
-    frames, seq_lens = preprocess_videos(raw, dimensions)
     net = ContactNet(state_dict)
-    labels, _ = net.forward(frames, seq_lens)
+    labels, _ = net.detect(raw, dimensions)
     written = []
     for i, v in enumerate(vids):
         od = os.path.join(out_root, "contact_results", v)
         os.makedirs(od, exist_ok=True)
-        np.save(os.path.join(od, "foot_contacts"), labels[i, :seq_lens[i]].astype(np.int64))
+        np.save(os.path.join(od, "foot_contacts"), labels[i].astype(np.int64))
         written.append(os.path.join(od, "foot_contacts.npy"))
     return written

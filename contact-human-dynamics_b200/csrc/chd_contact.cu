@@ -211,7 +211,11 @@ struct chd_contact_net {
   int64_t launches = 0;
   float* ws = nullptr;     // activation workspace of one slab: A0 [Mp][352] | A1 [Mp][1024] | A2 [Mp][512] | A3 [Mp][128]
   int ws_rows = 0;
+  // grow-only device buffers of the host entry points (no allocation per call, nothing to leak on an error path)
+  void* io[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t io_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+enum { IO_FRAMES = 0, IO_LENS = 1, IO_LABELS = 2, IO_LOGITS = 3, IO_MIN = 4, IO_RAW = 5, IO_OFFS = 6, IO_PACKED = 7 };
 
 #define CT_CUDA(x)                                                                           \
   do {                                                                                       \
@@ -221,6 +225,73 @@ struct chd_contact_net {
       return -100 - (int)e_;                                                                 \
     }                                                                                        \
   } while (0)
+
+// ------------------------------------------------------------------ keypoint preprocessing -----------------------
+// RealVideoDataset.__init__ (real_video_dataset.py:132-163) + process_openpose_data (openpose_dataset.py:49-121) on the
+// device: one thread per (video, joint) walks the frames of its joint.  raw: concatenated (sum F, 25, 3) [x, y, conf]
+// of the OpenPose json files, offs: V+1 frame offsets.  out: (V, Fmax, 25, 3) -- videos padded to the longest one
+// by repeating their last frame, xy scaled by 1280 / width, low-confidence (< thresh) runs of a joint replaced (leading /
+// trailing runs: nearest valid frame; interior runs: linear interpolation whose weight accumulates `cur += step` like the
+// reference loop), xy divided by the training normalisation.  Same fp64 operation order as the numpy reference
+// (explicit round-to-nearest multiplies / adds: no FMA contraction), so the result is bit identical.
+__global__ void chd_k_contact_prep(const double* __restrict__ raw, const int* __restrict__ offs, int V, int Fmax, double scale,
+                                   double norm, double thresh, double* __restrict__ out, int* __restrict__ seq_lens) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * 25) return;
+  const int v = idx / 25, j = idx % 25;
+  const int f0 = offs[v], len = offs[v + 1] - f0;
+  if (j == 0) seq_lens[v] = len;
+  auto src = [&](int t, int c) { return raw[((size_t)(f0 + (t < len ? t : len - 1)) * 25 + j) * 3 + c]; };
+  auto X = [&](int t, int c) { return __dmul_rn(src(t, c), scale); };   // a[:, :, :2] *= scale
+  double* o = out + ((size_t)v * Fmax * 25 + j) * 3;
+  const size_t fs = 25 * 3;
+  int t = 0;
+  while (t < Fmax) {
+    if (src(t, 2) < thresh) {
+      int nxt = t + 1;
+      while (nxt < Fmax && src(nxt, 2) < thresh) ++nxt;
+      const int init = t - 1;
+      for (int ct = t; ct < nxt; ++ct) {
+        double x, y;
+        if (t == 0 && nxt == Fmax) x = X(ct, 0), y = X(ct, 1);                    // never seen with confidence: left alone
+        else if (t == 0) x = X(nxt, 0), y = X(nxt, 1);                          // leading run: first valid frame
+        else if (nxt == Fmax) x = X(init, 0), y = X(init, 1);                   // trailing run: last valid frame
+        else {
+          const double step = 1.0 / (nxt - init);
+          double cur = step;
+          for (int q = t; q < ct; ++q) cur += step;                             // accumulated exactly like the reference loop
+          const double w0 = 1.0 - cur;
+          x = __dadd_rn(__dmul_rn(w0, X(init, 0)), __dmul_rn(cur, X(nxt, 0)));
+          y = __dadd_rn(__dmul_rn(w0, X(init, 1)), __dmul_rn(cur, X(nxt, 1)));
+        }
+        o[(size_t)ct * fs + 0] = x / norm, o[(size_t)ct * fs + 1] = y / norm, o[(size_t)ct * fs + 2] = src(ct, 2);
+      }
+      t = nxt;
+    } else {
+      o[(size_t)t * fs + 0] = X(t, 0) / norm, o[(size_t)t * fs + 1] = X(t, 1) / norm, o[(size_t)t * fs + 2] = src(t, 2);
+      ++t;
+    }
+  }
+}
+// (V, Fmax, 4) labels -> concatenated (sum F, 4), the rows foot_contacts.npy keeps (test.py:149-152)
+__global__ void chd_k_contact_pack(const long long* __restrict__ lab, const int* __restrict__ offs, int V, int Fmax, long long* __restrict__ out) {
+  const int v = blockIdx.y;
+  const int f0 = offs[v], len = offs[v + 1] - f0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len * 4; i += gridDim.x * blockDim.x) out[(size_t)f0 * 4 + i] = lab[(size_t)v * Fmax * 4 + i];
+}
+
+static int ct_reserve(chd_contact_net* net, int slot, size_t bytes) {
+  if (bytes <= net->io_bytes[slot]) return 0;
+  if (net->io[slot]) cudaFree(net->io[slot]);
+  net->io[slot] = nullptr, net->io_bytes[slot] = 0;
+  cudaError_t e = cudaMalloc(&net->io[slot], bytes);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "libchd: CUDA error %s (contact io buffer %d, %zu bytes)\n", cudaGetErrorString(e), slot, bytes);
+    return -100 - (int)e;
+  }
+  net->io_bytes[slot] = bytes;
+  return 0;
+}
 
 extern "C" {
 
@@ -270,13 +341,15 @@ void chd_contact_destroy(chd_contact_net* net) {
   if (!net) return;
   for (void* p : net->allocs) cudaFree(p);
   if (net->ws) cudaFree(net->ws);
+  for (int q = 0; q < 8; ++q)
+    if (net->io[q]) cudaFree(net->io[q]);
   if (net->stream) cudaStreamDestroy(net->stream);
   delete net;
 }
 
 int chd_contact_forward_device(chd_contact_net* net, const double* frames_dev, int32_t V, int32_t Fmax, const int32_t* seq_lens_dev,
                                int64_t* labels_dev, float* logits_dev, float* min_abs_dev, void* stream) {
-  if (!net || !frames_dev || Fmax < CT_WIN) return -1;
+  if (!net || !frames_dev || !seq_lens_dev || !labels_dev || !logits_dev || !min_abs_dev || Fmax < CT_WIN) return -1;   // all device buffers are required
   cudaStream_t s = stream ? (cudaStream_t)stream : net->stream;
   const int Wn = Fmax - (CT_WIN - 1), total = V * Wn;
   const float big = 3.4e38f;
@@ -312,24 +385,80 @@ int chd_contact_forward(chd_contact_net* net, const double* frames, int32_t V, i
                         float* logits, float* min_abs_logit) {
   if (!net || !frames || !seq_lens || !labels || V <= 0 || Fmax < CT_WIN) return -1;
   const size_t nfr = (size_t)V * Fmax * 75, Wn = Fmax - (CT_WIN - 1), nlog = (size_t)V * Wn * 20, nlab = (size_t)V * Fmax * 4;
-  double* d_fr = nullptr;
-  int* d_len = nullptr;
-  long long* d_lab = nullptr;
-  float *d_log = nullptr, *d_min = nullptr;
-  CT_CUDA(cudaMalloc((void**)&d_fr, nfr * sizeof(double)));
-  CT_CUDA(cudaMalloc((void**)&d_len, V * sizeof(int)));
-  CT_CUDA(cudaMalloc((void**)&d_lab, nlab * sizeof(long long)));
-  CT_CUDA(cudaMalloc((void**)&d_log, nlog * sizeof(float)));
-  CT_CUDA(cudaMalloc((void**)&d_min, sizeof(float)));
+  int rc;
+  if ((rc = ct_reserve(net, IO_FRAMES, nfr * sizeof(double))) || (rc = ct_reserve(net, IO_LENS, V * sizeof(int))) ||
+      (rc = ct_reserve(net, IO_LABELS, nlab * sizeof(long long))) || (rc = ct_reserve(net, IO_LOGITS, nlog * sizeof(float))) ||
+      (rc = ct_reserve(net, IO_MIN, sizeof(float))))
+    return rc;
+  double* d_fr = (double*)net->io[IO_FRAMES];
+  int* d_len = (int*)net->io[IO_LENS];
+  long long* d_lab = (long long*)net->io[IO_LABELS];
+  float *d_log = (float*)net->io[IO_LOGITS], *d_min = (float*)net->io[IO_MIN];
   CT_CUDA(cudaMemcpyAsync(d_fr, frames, nfr * sizeof(double), cudaMemcpyHostToDevice, net->stream));
   CT_CUDA(cudaMemcpyAsync(d_len, seq_lens, V * sizeof(int), cudaMemcpyHostToDevice, net->stream));
-  int rc = chd_contact_forward_device(net, d_fr, V, Fmax, d_len, (int64_t*)d_lab, d_log, d_min, net->stream);
+  rc = chd_contact_forward_device(net, d_fr, V, Fmax, d_len, (int64_t*)d_lab, d_log, d_min, net->stream);
   if (rc) return rc;
   CT_CUDA(cudaMemcpyAsync(labels, d_lab, nlab * sizeof(long long), cudaMemcpyDeviceToHost, net->stream));
   if (logits) CT_CUDA(cudaMemcpyAsync(logits, d_log, nlog * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
   if (min_abs_logit) CT_CUDA(cudaMemcpyAsync(min_abs_logit, d_min, sizeof(float), cudaMemcpyDeviceToHost, net->stream));
   CT_CUDA(cudaStreamSynchronize(net->stream));
-  cudaFree(d_fr), cudaFree(d_len), cudaFree(d_lab), cudaFree(d_log), cudaFree(d_min);
+  return 0;
+}
+
+// raw OpenPose keypoints -> preprocessed frames on the device (shared by chd_contact_preprocess / chd_contact_detect)
+static int ct_prep_device(chd_contact_net* net, const double* raw, const int32_t* offs, int32_t V, int32_t dim_w, int* Fmax_out) {
+  int Fmax = 0, total = offs[V];
+  for (int v = 0; v < V; ++v) {
+    if (offs[v + 1] <= offs[v]) return -1;
+    Fmax = std::max(Fmax, offs[v + 1] - offs[v]);
+  }
+  if (Fmax < CT_WIN) return -1;
+  int rc;
+  if ((rc = ct_reserve(net, IO_RAW, (size_t)total * 75 * sizeof(double))) || (rc = ct_reserve(net, IO_OFFS, (V + 1) * sizeof(int))) ||
+      (rc = ct_reserve(net, IO_FRAMES, (size_t)V * Fmax * 75 * sizeof(double))) || (rc = ct_reserve(net, IO_LENS, V * sizeof(int))))
+    return rc;
+  CT_CUDA(cudaMemcpyAsync(net->io[IO_RAW], raw, (size_t)total * 75 * sizeof(double), cudaMemcpyHostToDevice, net->stream));
+  CT_CUDA(cudaMemcpyAsync(net->io[IO_OFFS], offs, (V + 1) * sizeof(int), cudaMemcpyHostToDevice, net->stream));
+  const double scale = 1280.0 / dim_w;                       // TRAIN_DIM[0] / dimensions[0], real_video_dataset.py:17,149-155
+  chd_k_contact_prep<<<(V * 25 + 127) / 128, 128, 0, net->stream>>>((const double*)net->io[IO_RAW], (const int*)net->io[IO_OFFS], V, Fmax, scale,
+                                                                    200.4160302695367, 0.2, (double*)net->io[IO_FRAMES], (int*)net->io[IO_LENS]);
+  net->launches += 1;
+  CT_CUDA(cudaGetLastError());
+  *Fmax_out = Fmax;
+  return 0;
+}
+
+int chd_contact_preprocess(chd_contact_net* net, const double* raw, const int32_t* seq_offsets, int32_t V, int32_t dim_w, double* frames_out,
+                           int32_t* seq_lens_out) {
+  if (!net || !raw || !seq_offsets || V <= 0 || dim_w <= 0 || !frames_out) return -1;
+  int Fmax = 0;
+  int rc = ct_prep_device(net, raw, seq_offsets, V, dim_w, &Fmax);
+  if (rc) return rc;
+  CT_CUDA(cudaMemcpyAsync(frames_out, net->io[IO_FRAMES], (size_t)V * Fmax * 75 * sizeof(double), cudaMemcpyDeviceToHost, net->stream));
+  if (seq_lens_out) CT_CUDA(cudaMemcpyAsync(seq_lens_out, net->io[IO_LENS], V * sizeof(int), cudaMemcpyDeviceToHost, net->stream));
+  CT_CUDA(cudaStreamSynchronize(net->stream));
+  return 0;
+}
+
+int chd_contact_detect(chd_contact_net* net, const double* raw, const int32_t* seq_offsets, int32_t V, int32_t dim_w, int64_t* labels_out,
+                       float* min_abs_logit) {
+  if (!net || !raw || !seq_offsets || V <= 0 || dim_w <= 0 || !labels_out) return -1;
+  int Fmax = 0;
+  int rc = ct_prep_device(net, raw, seq_offsets, V, dim_w, &Fmax);
+  if (rc) return rc;
+  const size_t Wn = Fmax - (CT_WIN - 1), nlog = (size_t)V * Wn * 20, nlab = (size_t)V * Fmax * 4, total = seq_offsets[V];
+  if ((rc = ct_reserve(net, IO_LABELS, nlab * sizeof(long long))) || (rc = ct_reserve(net, IO_LOGITS, nlog * sizeof(float))) ||
+      (rc = ct_reserve(net, IO_MIN, sizeof(float))) || (rc = ct_reserve(net, IO_PACKED, total * 4 * sizeof(long long))))
+    return rc;
+  rc = chd_contact_forward_device(net, (const double*)net->io[IO_FRAMES], V, Fmax, (const int*)net->io[IO_LENS], (int64_t*)net->io[IO_LABELS],
+                                  (float*)net->io[IO_LOGITS], (float*)net->io[IO_MIN], net->stream);
+  if (rc) return rc;
+  chd_k_contact_pack<<<dim3(4, V), 256, 0, net->stream>>>((const long long*)net->io[IO_LABELS], (const int*)net->io[IO_OFFS], V, Fmax,
+                                                          (long long*)net->io[IO_PACKED]);
+  net->launches += 1;
+  CT_CUDA(cudaMemcpyAsync(labels_out, net->io[IO_PACKED], total * 4 * sizeof(long long), cudaMemcpyDeviceToHost, net->stream));
+  if (min_abs_logit) CT_CUDA(cudaMemcpyAsync(min_abs_logit, net->io[IO_MIN], sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+  CT_CUDA(cudaStreamSynchronize(net->stream));
   return 0;
 }
 

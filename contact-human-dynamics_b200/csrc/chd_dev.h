@@ -39,6 +39,8 @@ struct ChdIpm {
   double f, E0, viol_u, dual_u, compl_u;          // error measures at the current iterate
   double phi0, theta0, dphi, a_pr, a_du;          // line-search inputs produced by the KKT kernel
   double dbg[8];                                  // diagnostics of the last line search: alpha, backtracks, theta_t, phi_t, guard / trust refusals
+  double dw_floor;                                // current floor of delta_w (adaptive: CHD_AF_N)
+  int af_cnt, af_pad;                             // consecutive full steps taken at the floor
   double theta_ref;                               // theta at the first iteration of the stage (nonlinearity guard of stage 3)
   double filt[2 * CHD_FILT_MAX];
   double st_stat[6][4];                           // per stage at its end: f, E0 (scaled NLP error), unscaled constraint violation, unscaled dual infeasibility
@@ -110,6 +112,8 @@ struct ChdDev {
 #define CHD_DELTA_C 1e-8
 #define CHD_DW_POLISH 1.0   /* Levenberg-Marquardt weight of a feasibility-polish step (every test but the unscaled violation passes) */
 #define CHD_DW_MIN 1e-8
+#define CHD_AF_N 10          /* after this many consecutive full steps taken at the floor of delta_w the floor drops by 10x ... */
+#define CHD_AF_MIN 1e-10     /* ... down to this; any backtrack restores CHD_DW_MIN */
 #define CHD_DW_MAX 1e4
 #define CHD_DW_INC 4.0
 #define CHD_DW_DEC 3.0

@@ -70,6 +70,7 @@ __global__ void chd_k_stage_begin(ChdDev D) {
     if (!warm) I.mu = CHD_MU_INIT, I.sf = 1.0, I.delta_w = CHD_DELTA_W0;
     else I.delta_w = fmax(I.delta_w, CHD_DELTA_W0);
     I.mu_filter = -1.0;
+    I.dw_floor = CHD_DW_MIN, I.af_cnt = 0;
     for (int q = 0; q < 8; ++q) I.prof[q] = 0.0;
     for (int q = 40; q < 48; ++q) I.filt[q] = 0.0;
   }
@@ -321,7 +322,15 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D) {
     }
     if (!accepted) I.ls_fail += 1;
     // Levenberg-Marquardt style adaptation of the primal regularisation
-    if (ls == 0) I.delta_w = fmax(I.delta_w / CHD_DW_DEC, CHD_DW_MIN);
+    // adaptive floor: sequences that take full steps at the floor converge linearly at a rate set by the floor (the
+    // reduced Hessian along force directions is ~1e-10); after CHD_AF_N such steps in a row the floor drops by 10x,
+    // any backtrack restores it
+    if (ls == 0 && I.delta_w <= I.dw_floor * 1.0000001) {
+      if (++I.af_cnt >= CHD_AF_N) I.dw_floor = fmax(I.dw_floor * 0.1, CHD_AF_MIN), I.af_cnt = 0;
+    } else if (ls > 0) {
+      I.dw_floor = CHD_DW_MIN, I.af_cnt = 0;
+    }
+    if (ls == 0) I.delta_w = fmax(I.delta_w / CHD_DW_DEC, I.dw_floor);
     else I.delta_w = fmin(I.delta_w * pow(CHD_DW_INC, (double)min(ls, 3)), CHD_DW_MAX);
     I.iter += 1;
     I.step_ready = 0;

@@ -160,10 +160,23 @@ void chd_contact_destroy(chd_contact_net* net);
  * logits [host, optional] V x (Fmax-8) x 20; min_abs_logit [host, optional]: smallest |logit| that entered a vote. */
 int chd_contact_forward(chd_contact_net* net, const double* frames, int32_t V, int32_t Fmax, const int32_t* seq_lens,
                         int64_t* labels, float* logits, float* min_abs_logit);
-/* Same with every buffer already on the device (stream = cudaStream_t as void*, NULL = the net's own stream). */
+/* Same with every buffer already on the device (stream = cudaStream_t as void*, NULL = the net's own stream); all
+ * device buffers, logits_dev and min_abs_dev included, are required (they are workspace of the vote kernel). */
 int chd_contact_forward_device(chd_contact_net* net, const double* frames_dev, int32_t V, int32_t Fmax,
                                const int32_t* seq_lens_dev, int64_t* labels_dev, float* logits_dev, float* min_abs_dev,
                                void* stream);
+/* Dataset preprocessing on the device (RealVideoDataset.__init__, real_video_dataset.py:132-163, and
+ * process_openpose_data, openpose_dataset.py:49-121): raw [host] = concatenated OpenPose keypoints (sum F) x 25 x 3
+ * doubles [x, y, confidence] as load_keypoint_dir returns them, seq_offsets [host] V+1 frame offsets, dim_w = width of
+ * the source video (reference default 1920).  frames_out [host] V x Fmax x 25 x 3 (Fmax = longest video),
+ * seq_lens_out [host, optional] V.  Bit identical to the reference's numpy result. */
+int chd_contact_preprocess(chd_contact_net* net, const double* raw, const int32_t* seq_offsets, int32_t V, int32_t dim_w,
+                           double* frames_out, int32_t* seq_lens_out);
+/* test.py --full-video --save-contacts --real-data in one call: raw keypoints in, foot_contacts rows out.
+ * labels_out [host] (sum F) x 4 int64 (columns L heel, L toe, R heel, R toe; the rows every video's foot_contacts.npy
+ * holds, concatenated).  raw may be page-locked: the upload is asynchronous on the net's stream. */
+int chd_contact_detect(chd_contact_net* net, const double* raw, const int32_t* seq_offsets, int32_t V, int32_t dim_w,
+                       int64_t* labels_out, float* min_abs_logit);
 int64_t chd_contact_launch_count(const chd_contact_net* net);
 
 const char* chd_version(void);

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracle of the contact-classifier path.
 
-Restates, in numpy / torch fp32, the window construction of real_video_dataset.py:206-276, the layer list of
+Restates, in numpy / torch fp32, the dataset preprocessing of real_video_dataset.py:132-163 /
+openpose_dataset.py:49-121 (the checker of the product's `chd_k_contact_prep` kernel), the window construction of real_video_dataset.py:206-276, the layer list of
 models/openpose_only.py:29-44 (eval mode) and the vote aggregation of test.py:88-122.  PINNED: checked against the
 golden vectors produced by the reference's own code (tests/golden/make_contact_golden.py ->
 tests/golden/contact/contact_golden.npz) in tests/test_contact_cpu.py.
@@ -9,6 +10,63 @@ import numpy as np
 
 LOWER = [8, 9, 10, 11, 12, 13, 14, 19, 20, 21, 22, 23, 24]   # openpose_dataset.py:38
 LIN_IDS, BN_IDS = [0, 3, 6, 10, 13], [1, 4, 7, 11]
+
+
+TRAIN_DIM = (1280, 720)                      # real_video_dataset.py:17
+TRAIN_NORMALIZATION = 200.4160302695367      # real_video_dataset.py:18
+
+
+def interpolate_low_confidence(seq, thresh=0.2):
+    """process_openpose_data (openpose_dataset.py:49-111) for one (F,J,3) sequence, in place on xy: per joint, leading /
+    trailing low-confidence runs take the nearest confident frame, interior runs are blended between the confident
+    frames on either side with a weight that is accumulated step by step (the reference's rounding)."""
+    F, J = seq.shape[:2]
+    low = seq[:, :, 2] < thresh
+    for j in range(J):
+        runs, t = [], 0
+        while t < F:                       # maximal runs [a, b) of low-confidence frames
+            if low[t, j]:
+                b = t
+                while b < F and low[b, j]:
+                    b += 1
+                runs.append((t, b))
+                t = b
+            else:
+                t += 1
+        for a, b in runs:
+            if a == 0 and b == F:
+                continue
+            if a == 0:
+                seq[:b, j, :2] = seq[b, j, :2]
+            elif b == F:
+                seq[a - 1:, j, :2] = seq[a - 1, j, :2]
+            else:
+                left, right = seq[a - 1, j, :2].copy(), seq[b, j, :2].copy()
+                step = 1.0 / (b - (a - 1))
+                w = step
+                for t in range(a, b):
+                    seq[t, j, :2] = (1.0 - w) * left + w * right
+                    w += step
+    return seq
+
+
+def preprocess_videos(raw, dimensions=(1920, 1080)):
+    """RealVideoDataset.__init__ (real_video_dataset.py:132-163): pad every video to the longest by repeating the last
+    frame, scale xy by 1280/width, interpolate low-confidence joints, divide xy by the training normalisation.
+    Returns (frames (V,Fmax,25,3) fp64, seq_lens (V,) int32)."""
+    seq_lens = np.array([r.shape[0] for r in raw], dtype=np.int32)
+    Fmax = int(seq_lens.max())
+    out = np.zeros((len(raw), Fmax, 25, 3))
+    scale = float(TRAIN_DIM[0]) / dimensions[0]
+    for i, r in enumerate(raw):
+        a = np.array(r, dtype=np.float64)
+        if a.shape[0] < Fmax:
+            a = np.concatenate([a, np.repeat(a[-1:], Fmax - a.shape[0], axis=0)], axis=0)
+        a[:, :, :2] *= scale
+        a = interpolate_low_confidence(a, 0.2)
+        a[:, :, :2] /= TRAIN_NORMALIZATION
+        out[i] = a
+    return out, seq_lens
 
 
 def windows_from_frames(frames, window=9):

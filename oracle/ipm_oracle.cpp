@@ -429,6 +429,10 @@ struct Solver {
     const double nl_ke = dur_vars.empty() ? 0.0 : (getenv("CHD_NL_KE") ? atof(getenv("CHD_NL_KE")) : 1.0);   // stage 3 only (CHD_NL_GUARD in chd_dev.h)
     const double nl_fl = getenv("CHD_NL_FL") ? atof(getenv("CHD_NL_FL")) : 1e-4;
     double theta_ref = 0.0;
+    const int af_n = getenv("CHD_AF_N") ? atoi(getenv("CHD_AF_N")) : 10;   // CHD_AF_N / CHD_AF_MIN of the product (csrc/chd_dev.h)
+    const double af_min = getenv("CHD_AF_MIN") ? atof(getenv("CHD_AF_MIN")) : 1e-10;
+    double dw_floor = o.dw_min;
+    int af_cnt = 0;
     const double polish_dw = getenv("CHD_POLISH") ? atof(getenv("CHD_POLISH")) : 1.0;   // CHD_DW_POLISH of the product (csrc/chd_dev.h)
     int n_polish = 0;
     const double du_unobs = getenv("CHD_DU") ? atof(getenv("CHD_DU")) : 1e-4;   // CHD_DW_UNOBS of the product (csrc/chd_dev.h)
@@ -684,7 +688,17 @@ struct Solver {
         const double dec3 = (!dur_vars.empty() && getenv("CHD_DW_DEC3")) ? atof(getenv("CHD_DW_DEC3")) : o.dw_dec;
         const double inc3 = (!dur_vars.empty() && getenv("CHD_DW_INC3")) ? atof(getenv("CHD_DW_INC3")) : o.dw_inc;
         const int cap3 = (!dur_vars.empty() && getenv("CHD_LS_CAP3")) ? atoi(getenv("CHD_LS_CAP3")) : 3;
-        if (ls_f == 0) delta_w = std::max(delta_w / dec3, o.dw_min);
+        // adaptive floor of the Levenberg-Marquardt weight: after `af_n` consecutive full steps (no backtrack) taken at the
+        // floor the floor drops by 10x (not below af_min); any backtrack restores 1e-8
+        if (af_n > 0) {
+          if (ls == 0 && delta_w <= dw_floor * 1.0000001) {
+            if (++af_cnt >= af_n) dw_floor = std::max(dw_floor * 0.1, af_min), af_cnt = 0;
+          } else if (ls > 0) {
+            dw_floor = o.dw_min, af_cnt = 0;
+          }
+        }
+        const double fl = af_n > 0 ? dw_floor : o.dw_min;
+        if (ls_f == 0) delta_w = std::max(delta_w / dec3, fl);
         else delta_w = std::min(delta_w * std::pow(inc3, (double)std::min(ls_f, cap3)), o.dw_max);
         if (rt0 > 0.0) {
           if (nl_rej == 0) rho_tau = std::max(rho_tau / rt_dec, rt_min);

@@ -18,13 +18,15 @@ def golden():
     return g
 
 
-def test_product_preprocessing_bit_exact(chd, golden):
+def test_oracle_preprocessing_bit_exact(chd, golden):
+    """the numpy checker of the product's preprocessing kernel against the arrays the reference's RealVideoDataset made"""
+    from oracle import contact as oc
     raw = [golden["raw_" + n] for n in golden["names"]]
     raw = [r.copy() for r in raw]
     for r in raw:      # frame 5 of the longer clips had no detections in the JSON dir -> zeros (openpose_utils.py:60-62)
         if r.shape[0] > 45:
             r[5] = 0.0
-    frames, seq_lens = chd.contact.preprocess_videos(raw)
+    frames, seq_lens = oc.preprocess_videos(raw)
     assert list(seq_lens) == list(golden["seq_lens"])
     for i, n in enumerate(golden["names"]):
         np.testing.assert_array_equal(frames[i], golden["proc_" + n])

@@ -32,9 +32,15 @@ def test_large_batch_against_torch_reference(chd):
     from oracle import contact as oc
     sd = contact_weights(1)
     raw = [synth_keypoints(1000 + i, 60 + (i % 7)) for i in range(48)]
-    frames, seq_lens = chd.contact.preprocess_videos(raw)
     net = chd.contact.ContactNet(sd)
+    frames, seq_lens = net.preprocess(raw)
+    f_ref, l_ref = oc.preprocess_videos(raw)
+    np.testing.assert_array_equal(frames, f_ref)                       # device preprocessing: bit exact vs the numpy checker
+    np.testing.assert_array_equal(seq_lens, l_ref)
     labels, logits, mabs = net.forward(frames, seq_lens, want_logits=True)
+    det, _ = net.detect(raw)                                           # one-call path: same labels
+    for i in range(len(raw)):
+        np.testing.assert_array_equal(det[i], labels[i, :seq_lens[i]])
     ref_logits = oc.forward_torch(sd, oc.windows_from_frames(frames))
     np.testing.assert_allclose(logits, ref_logits, rtol=0, atol=5e-5)
     risky = 0
@@ -45,3 +51,23 @@ def test_large_batch_against_torch_reference(chd):
             assert np.abs(ref_logits[i]).min() < 1e-4
             risky += 1
     assert risky <= 1
+
+
+def test_device_preprocessing_matches_reference_golden(chd):
+    """chd_k_contact_prep (padding, scaling, low-confidence interpolation, normalisation on the device) against the arrays
+    the reference's own RealVideoDataset produced (tests/golden/make_contact_golden.py): bit exact."""
+    from make_contact_golden import contact_weights
+    g = dict(np.load(os.path.join(HERE, "golden", "contact", "contact_golden.npz")))
+    names = [str(n) for n in g["names"]]
+    raw = [g["raw_" + n].copy() for n in names]
+    for r in raw:      # frame 5 of the longer clips had no detections in the JSON dir -> zeros (openpose_utils.py:60-62)
+        if r.shape[0] > 45:
+            r[5] = 0.0
+    net = chd.contact.ContactNet(contact_weights(0))
+    frames, seq_lens = net.preprocess(raw)
+    assert list(seq_lens) == list(g["seq_lens"])
+    for i, n in enumerate(names):
+        np.testing.assert_array_equal(frames[i], g["proc_" + n])
+    det, _ = net.detect(raw)
+    for i, n in enumerate(names):
+        np.testing.assert_array_equal(det[i], g["contacts_" + n])
