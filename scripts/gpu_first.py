@@ -13,7 +13,7 @@ print("create %.3fs dims %s" % (time.time() - t0, b.dims))
 print("sizes n,m,slots,Na,nb,w:", b.sizes[:4].tolist())
 b.set_timing(True)
 tot = 0
-for st in ["1.1", "1.2", "2.1", "2.2", "4"]:
+for st in ["1.1", "1.2", "2.1", "2.2", "3"]:
     t0 = time.time()
     r = b.solve_stage(st)
     dt = time.time() - t0
