@@ -321,7 +321,8 @@ static int batch_create_impl(const chd_phys_problem* problems, int32_t batch, co
   AL(sc, mm) AL(dL, mm) AL(dU, mm) AL(s, mm) AL(y, mm) AL(zL, mm) AL(zU, mm) AL(ds, mm) AL(dy, mm) AL(dzL, mm) AL(dzU, mm)
   D.nbc_max = (hb.Na_max + 7) / 8;
   D.Q = (hb.w_max + 7) / 8 + 1;
-  D.Qfix = (hb.w_fix_max + 7) / 8 + 1;   // band tiles the fixed-duration stages work with (storage strides follow Q)
+  D.Qfix = (hb.w_fix_max + 7) / 8 + 1;
+  D.tma = getenv("CHD_TMA") ? atoi(getenv("CHD_TMA")) : 0;   // band tiles the fixed-duration stages work with (storage strides follow Q)
   D.nbt = (hb.nb_max + 1 + 7) / 8;
   D.win_tiles = std::max(D.Q * (D.Q + 1) / 2, 2 * D.Q);
   D.kstride = (size_t)D.nbc_max * D.Q * 64 + (size_t)D.nbc_max * D.nbt * 64 + (size_t)64 * D.nbt * D.nbt;
@@ -550,6 +551,7 @@ int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int
       double* s = stats + 8 * i;
       s[0] = I.f, s[1] = I.E0, s[2] = I.viol_u, s[3] = I.dual_u, s[4] = I.compl_u, s[5] = I.mu, s[6] = I.delta_w, s[7] = I.ls_fail;
     }
+    if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "chd prof factor loop (Mcycles, accumulated since batch creation) warp1: panel+barrier %.2f updates %.2f wait+barrier %.2f | warp0: panel+barrier %.2f diagonal %.2f wait+barrier %.2f\n", I.dbg[0]/1e6, I.dbg[1]/1e6, I.dbg[2]/1e6, I.dbg[3]/1e6, I.dbg[4]/1e6, I.dbg[5]/1e6);
     if (i == 0 && getenv("CHD_PROF")) fprintf(stderr, "chd prof (Mcycles) seq0 stage %d: err %.2f jasm %.2f hasm %.2f factor %.2f border %.2f back %.2f rec %.2f\n", stage, I.prof[0]/1e6, I.prof[1]/1e6, I.prof[2]/1e6, I.prof[3]/1e6, I.prof[4]/1e6, I.prof[5]/1e6, I.prof[6]/1e6);
   }
   return 0;

@@ -57,7 +57,8 @@ struct ChdStageDev {
 
 struct ChdDev {
   int B, S, Pmax, n_max, m_max, slots_max, sets_max, tab_max, F_max, Kd_max, Kr_max, Na_max, nb_max, w_max, par_stride,
-      n_ee_max, fo_max, Ph_max, win_smem, nbc_max, Q, Qfix, nbt, win_tiles, pan_doubles;
+      n_ee_max, fo_max, Ph_max, win_smem, nbc_max, Q, Qfix, nbt, win_tiles, pan_doubles,
+      tma;   // 1: the elimination window is streamed with TMA bulk copies by a producer warp (CHD_TMA=1), 0: cp.async chunks by all warps
   size_t kstride;                             // doubles per sequence of a tile-format KKT buffer (band | bord | corn)
   // ---- static layout ----
   const ChdSeq* seq;

@@ -621,6 +621,10 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   __shared__ unsigned short s_pairs[3000];
   __shared__ unsigned char s_cmp[CHD_KKT_THREADS / 32][64];   // per warp: rank -> id of the non-zero panel groups
   __shared__ __align__(16) double s_winv[2][64];   // inverse of the current / next diagonal tile factor, fragment order
+  __shared__ __align__(8) unsigned long long s_mbar;   // completion of the TMA bulk stream-in of one block row
+  unsigned mbar_phase = 0;
+  const bool use_tma = WS && D.tma;
+  if (use_tma && tid == 0) chd_mbar_init(&s_mbar, 1);
   const int GB = K.q, Gm = K.q + nbt_s, npairs = Gm * (Gm + 1) / 2;
   for (int p = tid; p < npairs && p < 3000; p += nt) {
     int gi = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
@@ -637,7 +641,13 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
   }
   __syncthreads();
   int kslot = 0, cur = 0;  // kslot = Kc % Q
+#ifdef CHD_PROFILE
+  long long pf_a = 0, pf_b = 0, pf_c = 0, pf_acc[3] = {0, 0, 0};
+#endif
   for (int Kc = 0; Kc < nbc; ++Kc, cur ^= 1) {
+#ifdef CHD_PROFILE
+    pf_a = clock64();
+#endif
     const int tq = min(K.q, nbc - 1 - Kc);          // band tiles below the diagonal tile
     const int* rs = s_rs[cur];
     // tile addresses: circular triangular window in shared memory, or in place in the global band / border storage
@@ -683,12 +693,17 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
     if (WS)
       for (int e = tid; e < 64; e += nt) K.band[(size_t)Kc * Qs * 64 + e] = Tkk[e];
     __syncthreads();
+#ifdef CHD_PROFILE
+    pf_b = clock64();
+#endif
     // (c) stream in block row Kc + Q (its slots are dead now), trailing updates on the fp64 tensor core;
     //     warp 0 takes the pair that completes the next diagonal tile and factors it right away
     const int In = Kc + Q;
-    if (WS && In < nbc) {
-      // 16-byte chunks; warp 0 goes straight to the diagonal tile (dedicating two warps to the stream-in was measured
-      // slower: 482 vs 470 ms of KKT time per benchmark step)
+    // Two stream-in variants (D.tma, environment CHD_TMA at batch creation; measured on the benchmark batch: 1.00 ms per
+    // launch with the per-thread cp.async chunks, 1.04 ms with the TMA producer warp, 1.21 ms when a lane of an updating
+    // warp issues the bulk copies, 1.11 ms with dynamically dealt update blocks):
+    if (WS && !use_tma && In < nbc) {
+      // 16-byte cp.async chunks by the warps 1..15; warp 0 goes straight to the diagonal tile
       for (int idx = tid - 32; idx < Q * 32 + nbt_s * 32; idx += nt - 32) {
         if (idx < 0) break;
         const int tile = idx >> 5, off = (idx & 31) * 2;
@@ -701,6 +716,22 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
         }
       }
     }
+    // TMA variant: the last warp is the producer of the shared-memory window -- it only streams (the trailing updates
+    // are dealt to the warps 1 .. nwarp-2), so no warp of the update loop is held up by the serial issue of the copies
+    const bool producer = use_tma && warp == nwarp - 1;
+    if (producer && In < nbc && lane == 0) {
+      // TMA bulk copies (cp.async.bulk + mbarrier): one thread streams the Q band tiles of block row In (512 contiguous
+      // bytes each in the block-column storage) and its border tiles (one contiguous piece) into the slots the pivot
+      // block row just vacated; the slots were last touched through the generic proxy (panel phase, before the barrier)
+      chd_fence_async_smem();
+      chd_mbar_expect(&s_mbar, (unsigned)((Q + nbt_s) * 512));
+      for (int tile = 0; tile < Q; ++tile) {
+        const int J = tile < GB ? Kc + 1 + tile : In;
+        double* dst = tile < GB ? win + (size_t)tri(kslot, rs[tile]) * 64 : Tkk;
+        chd_bulk_g2s(dst, K.band + ((size_t)J * Qs + (In - J)) * 64, 512u, &s_mbar);
+      }
+      chd_bulk_g2s(Bk, K.bord + (size_t)In * nbt * 64, (unsigned)(nbt_s * 512), &s_mbar);
+    }
     if (warp == 0) {
       if (tq >= 1) {
         double* Tn = band_tile(0, 0);
@@ -709,7 +740,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
         const bool ok = chd_tile_ldl(Tn, dinv + 8 * (cur ^ 1), s_winv[cur ^ 1], lane);
         if (!ok && lane == 0) s_fail = 1;
       }
-    } else {
+    } else if (!producer) {
       if (warp == 1) {
         for (int g = lane; g < GB; g += 32) {   // slot table of the next block column
           int v = kslot + 2 + g;
@@ -819,7 +850,7 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
           chd_tile_mma(c0, c1, X, Y, lane);
           Cc[0] = c0, Cc[1] = c1;
         };
-        const int step = nwarp - 1, r8 = (lane >> 2) * 8 + 2 * (lane & 3);
+        const int step = use_tma ? nwarp - 2 : nwarp - 1, r8 = (lane >> 2) * 8 + 2 * (lane & 3);
         if (compact) {
           // 2 x 2 register blocking over the compacted group list: one trip loads the operand fragments of two panel
           // rows (X) and two panel columns (Y) once and updates up to four target tiles with them -- the loop is
@@ -900,10 +931,25 @@ __device__ __forceinline__ void chd_kkt_body(const ChdDev& D) {
         }
       }
     }
-    chd_copy_wait(WS);
+#ifdef CHD_PROFILE
+    pf_c = clock64();
+#endif
+    if (use_tma && In < nbc) {
+      chd_mbar_wait(&s_mbar, mbar_phase);
+      mbar_phase ^= 1u;
+    } else {
+      chd_copy_wait(WS);
+    }
     __syncthreads();
     kslot = kslot + 1 == Q ? 0 : kslot + 1;
+#ifdef CHD_PROFILE
+    { const long long t_ = clock64(); pf_acc[0] += pf_b - pf_a, pf_acc[1] += pf_c - pf_b, pf_acc[2] += t_ - pf_c; }
+#endif
   }
+#ifdef CHD_PROFILE
+  if (tid == 32) I.dbg[0] += (double)pf_acc[0], I.dbg[1] += (double)pf_acc[1], I.dbg[2] += (double)pf_acc[2];   // warp 1: panel+barrier | own updates | wait+barrier
+  if (tid == 0) I.dbg[3] += (double)pf_acc[0], I.dbg[4] += (double)pf_acc[1], I.dbg[5] += (double)pf_acc[2];    // warp 0: panel+barrier | diagonal tile | wait+barrier
+#endif
   CHD_PROF(3);
   // dense LDL^T of the border Schur complement S = cc[0..nbl)^2 and solve S xb = rb (rb = row NBR of cc)
   for (int k = 0; k < nbl; ++k) {

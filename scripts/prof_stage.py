@@ -9,7 +9,7 @@ ps = [chd.synth.make_problem(s, n_frames=nf, n_ee=ne, dense=bool(dense)) for s i
 b = chd.phys.PhysBatch(ps)
 print(b.dims)
 b.set_timing(True)
-for st, mi in [("1.1", 50), ("1.2", 300), ("2.1", 7000), ("2.2", 2500), ("4", 7000)]:
+for st, mi in [("1.1", 50), ("1.2", 300), ("2.1", 7000), ("2.2", 2500), ("3", 2000)]:
     t0 = time.time()
     r = b.solve_stage(st, mi)
     print(st, "status", r["status"].tolist(), "iters", r["iters"].tolist(), "%.3f s" % (time.time() - t0))
