@@ -1,8 +1,8 @@
 """BASELINE.json configs[0] ("single clip: contact detect + phys_optim", plumbing): the two drop-in scripts chained
 through the reference's own files -- openpose_result/*.json -> foot_contacts.npy -> contact_info.txt (+ the three
-other phys_optim inputs) -> sol_out_*.txt / success_log.txt.  The step in between (towr_utils.prepare_input: BVH
-FK, inertia, label clean-up) is not built, so the motion side of the clip is synthetic and a
-5-frame majority filter stands in for the label clean-up."""
+other phys_optim inputs) -> sol_out_*.txt / success_log.txt.  First test: the motion side of the clip is synthetic
+(chd.synth) and a 5-frame majority filter stands in for the label clean-up; second test: the step in between
+(towr_utils.prepare_input, chd.prepare) turns a BVH clip + floor file + foot_contacts.npy into the four input files."""
 import json
 import os
 import subprocess
@@ -67,3 +67,34 @@ def test_single_clip_files_end_to_end(chd, tmp_path):
         interior[ch + 1] = False
     interior[-1] = False
     np.testing.assert_array_equal(flags[interior], toe.T[interior])
+
+
+def test_bvh_clip_through_prepare_input(chd, tmp_path):
+    """BVH clip -> chd.prepare.prepare_input (FK, COM, hip offsets, inertia, contact schedule) -> phys_optim_in_* ->
+    scripts/phys_optim.py -> phys_optim_out_* -> chd.prepare.load_results (towr_utils.py:451-777, 51-122)."""
+    P = chd.prepare
+    F = 90
+    bvh = str(tmp_path / "walk.bvh")
+    P.write_test_bvh(bvh, F, seed=1)
+    with open(tmp_path / "floor_out.txt", "w") as f:
+        f.write("0.0 -1.0 0.0\n0.0 0.0 0.0\n")
+    t = np.arange(F)
+    period = 33                                           # frames per stride of the generated clip (0.9 Hz at 30 fps)
+    fc = np.zeros((F, 4), np.int64)                       # L heel, L toe, R heel, R toe
+    for col, shift in ((0, 0), (1, 2), (2, period // 2), (3, period // 2 + 2)):
+        fc[:, col] = ((t + shift) % period) < 20
+    fc[:2], fc[-3:] = fc[2], fc[-4]
+    np.save(tmp_path / "foot_contacts.npy", fc)
+    ind, outd = str(tmp_path / "phys_optim_in_biped"), str(tmp_path / "phys_optim_out_biped")
+    os.makedirs(outd)
+    p = P.prepare_input(bvh, str(tmp_path / "floor_out.txt"), str(tmp_path / "foot_contacts.npy"), ind, P.simple_biped_info())
+    assert p.n_frames == F and p.n_ee == 4
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "phys_optim.py"), "--in_dir", ind, "--nframes", str(F),
+                           "--out_dir", outd])
+    r = P.load_results(outd)
+    assert set(r) == {"no_dynamics", "dynamics", "durations", "success"}
+    for key in ("no_dynamics", "dynamics", "durations"):
+        assert r[key]["num_frames"] == F and r[key]["num_feet"] == 4
+        assert all(np.isfinite(np.asarray(v, float)).all() for v in r[key].values() if isinstance(v, np.ndarray))
+    # the kinematic stage tracks the prepared COM (z up, metres)
+    assert np.abs(r["no_dynamics"]["base_lin"] - p.base_lin).max() < 0.1
