@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of wall clock the CPU arm aims for")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-named", action="store_true", help="skip the 1024-sequence pass at 8 GPUs")
+    ap.add_argument("--named-world", type=int, default=8, help="world size at which the 128-per-GPU pass runs (8 = BASELINE configs[3])")
     args = ap.parse_args()
     rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
     if args.workload == "contact":
@@ -310,7 +311,7 @@ def main():
     e2e_total = float(reduce_max([sum(e2e_t)])[0])
 
     named = None
-    if world == 8 and args.workload == "phys" and per_gpu != 128 and not args.no_named:
+    if world == args.named_world and args.workload == "phys" and per_gpu != 128 and not args.no_named:
         # BASELINE.json configs[3]: 1024 sequences x 120 frames sharded across 8 B200 (128 per GPU)
         solver.close()
         Mn = measure(128, max(1, min(args.steps, 5)), 1, False)
