@@ -40,7 +40,9 @@ struct ChdIpm {
   double phi0, theta0, dphi, a_pr, a_du;          // line-search inputs produced by the KKT kernel
   double dbg[8];                                  // diagnostics of the last line search: alpha, backtracks, theta_t, phi_t, guard / trust refusals
   double dw_floor;                                // current floor of delta_w (adaptive: CHD_AF_N)
-  int af_cnt, af_pad;                             // consecutive full steps taken at the floor
+  int af_cnt, af_off;                             // consecutive full steps taken at the floor; 1: the lowered floor was taken back for this stage
+  int af_it, af_pad;                              // iteration of the first drop of the floor
+  double af_E;                                    // scaled error at that iteration
   double theta_ref;                               // theta at the first iteration of the stage (nonlinearity guard of stage 3)
   double filt[2 * CHD_FILT_MAX];
   double st_stat[6][4];                           // per stage at its end: f, E0 (scaled NLP error), unscaled constraint violation, unscaled dual infeasibility
@@ -114,7 +116,7 @@ struct ChdDev {
 #define CHD_DW_POLISH 1.0   /* Levenberg-Marquardt weight of a feasibility-polish step (every test but the unscaled violation passes) */
 #define CHD_DW_MIN 1e-8
 #define CHD_AF_N 10          /* after this many consecutive full steps taken at the floor of delta_w the floor drops by 10x ... */
-#define CHD_AF_MIN 1e-10     /* ... down to this; any backtrack restores CHD_DW_MIN */
+#define CHD_AF_MIN 1e-10     /* ... down to this; a backtrack, or an error that has not halved after 30 iterations, restores CHD_DW_MIN for the stage */
 #define CHD_DW_MAX 1e4
 #define CHD_DW_INC 4.0
 #define CHD_DW_DEC 3.0

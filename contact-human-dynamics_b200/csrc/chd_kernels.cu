@@ -70,7 +70,7 @@ __global__ void chd_k_stage_begin(ChdDev D) {
     if (!warm) I.mu = CHD_MU_INIT, I.sf = 1.0, I.delta_w = CHD_DELTA_W0;
     else I.delta_w = fmax(I.delta_w, CHD_DELTA_W0);
     I.mu_filter = -1.0;
-    I.dw_floor = CHD_DW_MIN, I.af_cnt = 0;
+    I.dw_floor = CHD_DW_MIN, I.af_cnt = 0, I.af_off = 0, I.af_it = 0, I.af_E = 0.0;
     for (int q = 0; q < 8; ++q) I.prof[q] = 0.0;
     for (int q = 40; q < 48; ++q) I.filt[q] = 0.0;
   }
@@ -324,13 +324,21 @@ __global__ void __launch_bounds__(CHD_THREADS) chd_k_linesearch(ChdDev D) {
     }
     if (!accepted) I.ls_fail += 1;
     // Levenberg-Marquardt style adaptation of the primal regularisation
-    // adaptive floor: sequences that take full steps at the floor converge linearly at a rate set by the floor (the
-    // reduced Hessian along force directions is ~1e-10); after CHD_AF_N such steps in a row the floor drops by 10x,
-    // any backtrack restores it
-    if (ls == 0 && I.delta_w <= I.dw_floor * 1.0000001) {
-      if (++I.af_cnt >= CHD_AF_N) I.dw_floor = fmax(I.dw_floor * 0.1, CHD_AF_MIN), I.af_cnt = 0;
-    } else if (ls > 0) {
-      I.dw_floor = CHD_DW_MIN, I.af_cnt = 0;
+    // Adaptive floor of the Levenberg-Marquardt weight.  Sequences that take full steps at the floor converge linearly at
+    // a rate set by the floor (the reduced Hessian along force directions is ~1e-10): after CHD_AF_N such steps in a row
+    // the floor drops by 10x (not below CHD_AF_MIN).  The lower floor is a gamble (the Gauss-Newton model misses
+    // constraint curvature: some sequences start to oscillate or crawl), so it is taken back for the rest of the stage
+    // at the first backtrack, or when the scaled error has not halved 30 iterations after the first drop.
+    if (!I.af_off) {
+      const bool at_floor = ls == 0 && I.delta_w <= I.dw_floor * 1.0000001;
+      if (I.dw_floor < CHD_DW_MIN) {
+        if (ls > 0 || (I.iter - I.af_it >= 30 && I.E0 > 0.5 * I.af_E)) I.dw_floor = CHD_DW_MIN, I.af_off = 1;
+        else if (at_floor && ++I.af_cnt >= CHD_AF_N) I.dw_floor = fmax(I.dw_floor * 0.1, CHD_AF_MIN), I.af_cnt = 0;
+      } else if (at_floor) {
+        if (++I.af_cnt >= CHD_AF_N) I.dw_floor = fmax(I.dw_floor * 0.1, CHD_AF_MIN), I.af_cnt = 0, I.af_E = I.E0, I.af_it = I.iter;
+      } else if (ls > 0) {
+        I.af_cnt = 0;
+      }
     }
     if (ls == 0) I.delta_w = fmax(I.delta_w / CHD_DW_DEC, I.dw_floor);
     else I.delta_w = fmin(I.delta_w * pow(CHD_DW_INC, (double)min(ls, 3)), CHD_DW_MAX);

@@ -431,8 +431,9 @@ struct Solver {
     double theta_ref = 0.0;
     const int af_n = getenv("CHD_AF_N") ? atoi(getenv("CHD_AF_N")) : 10;   // CHD_AF_N / CHD_AF_MIN of the product (csrc/chd_dev.h)
     const double af_min = getenv("CHD_AF_MIN") ? atof(getenv("CHD_AF_MIN")) : 1e-10;
-    double dw_floor = o.dw_min;
-    int af_cnt = 0;
+    double dw_floor = o.dw_min, af_E = 0.0;
+    int af_cnt = 0, af_it = 0;
+    bool af_off = false;
     const double polish_dw = getenv("CHD_POLISH") ? atof(getenv("CHD_POLISH")) : 1.0;   // CHD_DW_POLISH of the product (csrc/chd_dev.h)
     int n_polish = 0;
     const double du_unobs = getenv("CHD_DU") ? atof(getenv("CHD_DU")) : 1e-4;   // CHD_DW_UNOBS of the product (csrc/chd_dev.h)
@@ -688,13 +689,20 @@ struct Solver {
         const double dec3 = (!dur_vars.empty() && getenv("CHD_DW_DEC3")) ? atof(getenv("CHD_DW_DEC3")) : o.dw_dec;
         const double inc3 = (!dur_vars.empty() && getenv("CHD_DW_INC3")) ? atof(getenv("CHD_DW_INC3")) : o.dw_inc;
         const int cap3 = (!dur_vars.empty() && getenv("CHD_LS_CAP3")) ? atoi(getenv("CHD_LS_CAP3")) : 3;
-        // adaptive floor of the Levenberg-Marquardt weight: after `af_n` consecutive full steps (no backtrack) taken at the
-        // floor the floor drops by 10x (not below af_min); any backtrack restores 1e-8
-        if (af_n > 0) {
-          if (ls == 0 && delta_w <= dw_floor * 1.0000001) {
-            if (++af_cnt >= af_n) dw_floor = std::max(dw_floor * 0.1, af_min), af_cnt = 0;
+        // Adaptive floor of the Levenberg-Marquardt weight.  Sequences that take full steps at the floor converge linearly
+        // at a rate set by the floor (the reduced Hessian along force directions is ~1e-10): after `af_n` such steps in a
+        // row the floor drops by 10x (not below af_min).  The lower floor is a gamble (the Gauss-Newton model misses
+        // constraint curvature: some sequences start to oscillate or crawl), so it is taken back for the rest of the
+        // stage at the first backtrack, or when the scaled error has not halved 30 iterations after the first drop.
+        if (af_n > 0 && !af_off) {
+          const bool at_floor = ls == 0 && delta_w <= dw_floor * 1.0000001;
+          if (dw_floor < o.dw_min) {
+            if (ls > 0 || (it - af_it >= 30 && E0 > 0.5 * af_E)) dw_floor = o.dw_min, af_off = true;
+            else if (at_floor && ++af_cnt >= af_n) dw_floor = std::max(dw_floor * 0.1, af_min), af_cnt = 0;
+          } else if (at_floor) {
+            if (++af_cnt >= af_n) dw_floor = std::max(dw_floor * 0.1, af_min), af_cnt = 0, af_E = E0, af_it = it;
           } else if (ls > 0) {
-            dw_floor = o.dw_min, af_cnt = 0;
+            af_cnt = 0;
           }
         }
         const double fl = af_n > 0 ? dw_floor : o.dw_min;
