@@ -81,7 +81,7 @@ __global__ void chd_k_stage_begin(ChdDev D) {
 __global__ void __launch_bounds__(CHD_THREADS) chd_k_eval(ChdDev D) {
   extern __shared__ double sm[];
   const int b = blockIdx.x;
-  if (D.ipm[b].phase == CHD_PH_FINISHED) return;
+  if (D.ipm[b].phase != CHD_PH_BEGIN && D.ipm[b].phase != CHD_PH_RUN) return;
   const ChdStageDev sg = D.stages[D.ipm[b].stage];
   const ChdSeq* h = D.seq + b;
   double* xs = sm;
@@ -438,6 +438,9 @@ __global__ void chd_k_sched_reset(ChdDev D) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= D.B) return;
   ChdIpm& I = D.ipm[b];
-  I.pos = 0, I.stage = D.sched[0], I.phase = CHD_PH_BEGIN, I.snap = -1, I.step_ready = 0, I.kw_req = 0, I.status = 1;
+  // the first `slots` sequences start, the others wait for a slot (one CTA per SM can be resident: more running
+  // sequences than that would only add waves of mostly finished CTAs to every launch)
+  I.pos = 0, I.stage = D.sched[0], I.phase = b < D.queue[1] ? CHD_PH_BEGIN : CHD_PH_WAITING, I.snap = -1, I.step_ready = 0, I.kw_req = 0, I.status = 1;
+  if (b == 0) D.queue[0] = D.queue[1] < D.B ? D.queue[1] : D.B;
   for (int q = 0; q < 6; ++q) I.st_status[q] = -9, I.st_iters[q] = 0;
 }
