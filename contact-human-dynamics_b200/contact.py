@@ -8,7 +8,6 @@ and the vote aggregation run in hand-written CUDA behind `chd_contact_*` (includ
 from __future__ import annotations
 
 import ctypes as C
-import json
 import os
 from typing import Dict, List, Sequence
 
@@ -23,19 +22,43 @@ LIN_IDS, BN_IDS = [0, 3, 6, 10, 13], [1, 4, 7, 11]
 DIMS = [351, 1024, 512, 128, 32, 20]
 
 
+def load_keypoint_files(files: Sequence[str], num_joints: int = 25, threads: int = 0) -> np.ndarray:
+    """Many OpenPose `*_keypoints.json` files -> (len(files), J, 3) fp64 through the native threaded reader
+    (`chd_openpose_load`, csrc/chd_openpose.cpp); bit-identical to openpose_utils.py:48-66 applied per file."""
+    L = load_lib()
+    out = np.empty((len(files), num_joints, 3), dtype=np.float64)
+    arr = (C.c_char_p * len(files))(*[os.fsencode(f) for f in files])
+    L.chd_openpose_load.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+    rc = L.chd_openpose_load(arr, len(files), num_joints, out.ctypes.data_as(C.c_void_p), threads)
+    if rc:
+        raise RuntimeError("chd_openpose_load failed: %d (-2 unreadable file, -3 malformed keypoint file)" % rc)
+    return out
+
+
 def load_keypoint_file(path: str, num_joints: int = 25) -> np.ndarray:
     """openpose_utils.py:48-66: first person's pose_keypoints_2d as (J,3); zeros if nobody was detected."""
-    with open(path) as f:
-        d = json.load(f)
-    if len(d["people"]) == 0:
-        return np.zeros((num_joints, 3))
-    return np.array(d["people"][0]["pose_keypoints_2d"], dtype=np.float64).reshape(-1, 3)
+    return load_keypoint_files([path], num_joints)[0]
+
+
+def keypoint_files(path: str) -> List[str]:
+    """openpose_utils.py:72: the *.json of a directory in sorted order."""
+    return sorted(os.path.join(path, f) for f in os.listdir(path) if f.split(".")[-1] == "json")
 
 
 def load_keypoint_dir(path: str) -> np.ndarray:
     """openpose_utils.py:68-76: all *.json of a directory in sorted order -> (F,25,3)."""
-    files = sorted(os.path.join(path, f) for f in os.listdir(path) if f.split(".")[-1] == "json")
-    return np.stack([load_keypoint_file(f) for f in files], axis=0)
+    return load_keypoint_files(keypoint_files(path))
+
+
+def load_keypoint_dirs(paths: Sequence[str], threads: int = 0) -> List[np.ndarray]:
+    """Several videos at once: one pass of the threaded reader over all files of all directories."""
+    lists = [keypoint_files(p) for p in paths]
+    flat = load_keypoint_files([f for l in lists for f in l], threads=threads)
+    out, o = [], 0
+    for l in lists:
+        out.append(flat[o:o + len(l)])
+        o += len(l)
+    return out
 
 
 def concat_videos(raw: Sequence[np.ndarray]):
@@ -142,7 +165,7 @@ def detect_contacts(data_root: str, out_root: str, state_dict, dimensions=(1920,
     """`test.py --data D --out O --full-video --save-contacts --real-data`: for every video directory of D with an
     `openpose_result/` writes O/contact_results/<video>/foot_contacts.npy (int64, F x 4), test.py:143-152."""
     vids = sorted(d for d in os.listdir(data_root) if os.path.isdir(os.path.join(data_root, d)) and d[0] != ".")
-    raw = [load_keypoint_dir(os.path.join(data_root, v, "openpose_result")) for v in vids]
+    raw = load_keypoint_dirs([os.path.join(data_root, v, "openpose_result") for v in vids])
     net = ContactNet(state_dict)
     labels, _ = net.detect(raw, dimensions)
     written = []

@@ -179,6 +179,13 @@ int chd_contact_detect(chd_contact_net* net, const double* raw, const int32_t* s
                        int64_t* labels_out, float* min_abs_logit);
 int64_t chd_contact_launch_count(const chd_contact_net* net);
 
+/* OpenPose keypoint ingestion on the host threads (replaces the serial per-file json.load of
+ * src/utils/openpose_utils.py:48-76 load_keypoint_file / load_keypoint_dir): n_files `*_keypoints.json` files ->
+ * out [host] n_files x num_joints x 3 fp64 (x, y, confidence of the FIRST person's "pose_keypoints_2d"; zeros for a frame
+ * without people), bit-identical to the reference's arrays (strtod).  n_threads <= 0: all hardware threads.
+ * Returns 0, -1 bad argument, -2 unreadable file, -3 malformed file / keypoint count != 3 * num_joints. */
+int chd_openpose_load(const char* const* paths, int32_t n_files, int32_t num_joints, double* out, int32_t n_threads);
+
 const char* chd_version(void);
 
 /* Measurement helper (no reference counterpart): sustained fp64 throughput of the current device in GFLOP/s, for the
