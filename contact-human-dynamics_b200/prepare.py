@@ -42,6 +42,7 @@ class CharacterInfo:
     segment_mass_percent: Dict[str, float]
     mass: float = MALE_MASS
     heel_inds: Optional[Tuple[int, int]] = None   # skeletons that already carry heel joints
+    upper_body_joints: Optional[List[int]] = None  # incl. the root: what apply_results pins to the optimised COM
 
     @property
     def hips(self):
@@ -54,6 +55,38 @@ class CharacterInfo:
     @property
     def ankles(self):
         return [self.left_leg_chain[-2], self.right_leg_chain[-2]]
+
+
+# Zatsiorsky - de Leva segment mass percentages, male (character_info_utils.py:143-160)
+MASS_PERCENT_MALE = {"head": 6.94, "upper_trunk": 15.96, "mid_trunk": 16.33, "lower_trunk": 11.17, "left_upper_arm": 2.71,
+                     "left_forearm": 1.62, "left_hand": 0.61, "left_thigh": 14.16, "left_shank": 4.33, "left_foot": 1.37,
+                     "right_upper_arm": 2.71, "right_forearm": 1.62, "right_hand": 0.61, "right_thigh": 14.16, "right_shank": 4.33,
+                     "right_foot": 1.37}
+
+
+def _segments(head, ut, mt, lt, lua, lfa, lh, lth, lsh, lf, rua, rfa, rh, rth, rsh, rf):
+    keys = list(MASS_PERCENT_MALE.keys())
+    return dict(zip(keys, [list(v) for v in (head, ut, mt, lt, lua, lfa, lh, lth, lsh, lf, rua, rfa, rh, rth, rsh, rf)]))
+
+
+def combined_info() -> "CharacterInfo":
+    """The reference's `combined` skeleton (OpenPose body + SMPL spine, 28 joints, own heel joints):
+    character_info_utils.py:257-287."""
+    return CharacterInfo(left_leg_chain=[1, 2, 3, 5], right_leg_chain=[7, 8, 9, 11],
+                         segment_to_joints=_segments([17], [15, 16], [14, 15], [13, 14], [22, 23], [23, 24], [24], [1, 2], [2, 3], [3, 4, 5, 6],
+                                                     [25, 26], [26, 27], [27], [7, 8], [8, 9], [9, 10, 11, 12]),
+                         segment_mass_percent=dict(MASS_PERCENT_MALE), heel_inds=(4, 10), upper_body_joints=[0] + list(range(13, 28)))
+
+
+def ybot_info() -> "CharacterInfo":
+    """The reference's Mixamo `ybot` character (67 joints, no heel joints): character_info_utils.py:294-321."""
+    return CharacterInfo(left_leg_chain=[62, 63, 64, 65], right_leg_chain=[57, 58, 59, 60],
+                         segment_to_joints=_segments([5], [3], [2], [1], [10, 11], [11, 12], range(12, 33), [62, 63], [63, 64], [64, 65, 66],
+                                                     [34, 35], [35, 36], range(36, 57), [57, 58], [58, 59], [59, 60, 61]),
+                         segment_mass_percent=dict(MASS_PERCENT_MALE), upper_body_joints=list(range(0, 57)))
+
+
+CHARACTERS = {"combined": combined_info, "ybot": ybot_info}
 
 
 @dataclass
@@ -313,6 +346,38 @@ def load_results(res_dir: str, nframes: Optional[int] = None) -> dict:
         vals = open(log).read().split()
         out["success"] = {vals[0]: int(vals[1]), vals[2]: int(vals[3])}
     return out
+
+
+def write_bvh(path: str, names, parents, offsets, rows, frame_time: float, order: str = "ZXY", end_site=(0.0, 0.0, 0.0)):
+    """BVH writer: root with 6 channels (XYZ position + rotations in `order`), 3 rotation channels per joint, joints in
+    depth-first order (which must be the index order, as every BVH reader assumes); `rows` = (F, 3 + 3 J) channel values
+    in degrees.  Six decimals like the reference's `BVH.save` (BVH.py:174-248), which also writes root-only positions."""
+    J = len(names)
+    children = {j: [c for c in range(J) if parents[c] == j] for j in range(J)}
+    chan = " ".join(a + "rotation" for a in order)
+    lines, seen = ["HIERARCHY"], []
+
+    def emit(j, depth):
+        seen.append(j)
+        ind = "\t" * depth
+        lines.append("%s%s %s" % (ind, "ROOT" if depth == 0 else "JOINT", names[j]))
+        lines.append(ind + "{")
+        lines.append("%s\tOFFSET %f %f %f" % ((ind,) + tuple(float(v) for v in offsets[j])))
+        lines.append("%s\tCHANNELS %s" % (ind, ("6 Xposition Yposition Zposition " if depth == 0 else "3 ") + chan))
+        if not children[j]:
+            lines.extend([ind + "\tEnd Site", ind + "\t{", "%s\t\tOFFSET %f %f %f" % ((ind,) + tuple(end_site)), ind + "\t}"])
+        for c in children[j]:
+            emit(c, depth + 1)
+        lines.append(ind + "}")
+
+    emit(0, 0)
+    if seen != list(range(J)):
+        raise ValueError("joint indices must follow the depth-first order of the hierarchy")
+    rows = np.asarray(rows, dtype=np.float64)
+    lines += ["MOTION", "Frames: %d" % rows.shape[0], "Frame Time: %f" % frame_time]
+    lines += [" ".join("%f" % v for v in r) for r in rows]
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
