@@ -128,9 +128,10 @@ def descendants_mask(parents) -> np.ndarray:
 
 
 def ik_solve(anim: SkelAnim, targets: Dict[int, np.ndarray], iterations: int = 30, damping: float = 7.0, smoothness: float = 0.001,
-             device=None, gamma: float = 1.0, history: Optional[list] = None) -> SkelAnim:
-    """Damped least-squares full-body IK with translating joints (JacobianInverseKinematicsCK, translate=True, unit
-    weights, no references / angle limits), all frames at once.  `targets`: joint index -> (F, 3) world positions."""
+             device=None, gamma: float = 1.0, history: Optional[list] = None, translate: bool = True) -> SkelAnim:
+    """Damped least-squares full-body IK (JacobianInverseKinematicsCK, unit weights, no references / angle limits), all
+    frames at once; `translate`: the joints' local translations are unknowns too.  `targets`: joint index -> (F, 3)
+    world positions."""
     import torch
     dev = torch.device(device) if device is not None else torch.device("cpu")
     f64 = dict(dtype=torch.float64, device=dev)
@@ -173,7 +174,7 @@ def ik_solve(anim: SkelAnim, targets: Dict[int, np.ndarray], iterations: int = 3
     for it in range(iterations):
         gR, gP = fk(Rl, Pl)
         e = euler_of(Rl)                                               # (F, J, 3)
-        x = torch.cat([e.reshape(F, -1), Pl.reshape(F, -1)], dim=1)    # (F, 6J)
+        x = torch.cat([e.reshape(F, -1), Pl.reshape(F, -1)], dim=1) if translate else e.reshape(F, -1)   # (F, 6J) / (F, 3J)
         prs = gR[:, par_idx].clone()                                   # parent's global rotation, identity for the root
         prs[:, root_mask] = eye3
         cz, sz, cy, sy = torch.cos(e[..., 2]), torch.sin(e[..., 2]), torch.cos(e[..., 1]), torch.sin(e[..., 1])
@@ -187,8 +188,11 @@ def ik_solve(anim: SkelAnim, targets: Dict[int, np.ndarray], iterations: int = 3
         tp = gP[:, tj]                                                 # (F, T, 3)
         arm = tp[:, None, :, :] - gP[:, :, None, :]                    # (F, J, T, 3) target minus joint position
         jr = torch.cross(axes[:, :, :, None, :].expand(F, J, 3, T, 3), arm[:, :, None, :, :].expand(F, J, 3, T, 3), dim=-1) * dsc[None, :, None, :, None]
-        jt = prs.transpose(-1, -2)[:, :, :, None, :].expand(F, J, 3, T, 3) * tdsc[None, :, None, :, None]   # column a of prs = prs e_a
-        Jm = torch.cat([jr.reshape(F, 3 * J, 3 * T), jt.reshape(F, 3 * J, 3 * T)], dim=1).transpose(1, 2)     # (F, 3T, 6J)
+        if translate:
+            jt = prs.transpose(-1, -2)[:, :, :, None, :].expand(F, J, 3, T, 3) * tdsc[None, :, None, :, None]   # column a of prs = prs e_a
+            Jm = torch.cat([jr.reshape(F, 3 * J, 3 * T), jt.reshape(F, 3 * J, 3 * T)], dim=1).transpose(1, 2)     # (F, 3T, 6J)
+        else:
+            Jm = jr.reshape(F, 3 * J, 3 * T).transpose(1, 2)
         err = gamma * (goal - tp).reshape(F, 3 * T)
         if history is not None:
             history.append(float(torch.sqrt(((goal - tp) ** 2).sum(-1)).mean()))
@@ -199,7 +203,8 @@ def ik_solve(anim: SkelAnim, targets: Dict[int, np.ndarray], iterations: int = 3
         xa = torch.cat([x[1:], x[-1:]], dim=0)
         x = x + dx1 + smoothness * (xp + xa - 2.0 * x)
         Rl = rot_of(x[:, :3 * J].reshape(F, J, 3))
-        Pl = x[:, 3 * J:].reshape(F, J, 3)
+        if translate:
+            Pl = x[:, 3 * J:].reshape(F, J, 3)
     if history is not None:
         _, gP = fk(Rl, Pl)
         history.append(float(torch.sqrt(((goal - gP[:, tj]) ** 2).sum(-1)).mean()))

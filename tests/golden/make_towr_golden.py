@@ -38,9 +38,10 @@ def import_reference():
     ut.inner1d = lambda a, b: np.einsum("...i,...i->...", a, b)
     ut.matrix_multiply = np.matmul
     sys.modules["numpy.core.umath_tests"] = ut
-    for m in ["matplotlib", "matplotlib.pyplot", "matplotlib.animation", "matplotlib.patheffects", "mpl_toolkits",
-              "mpl_toolkits.mplot3d", "skimage", "skimage.io", "skimage.transform", "cv2"]:
+    for m in ["matplotlib", "matplotlib.pyplot", "matplotlib.animation", "matplotlib.patheffects", "matplotlib.colors", "matplotlib.cm",
+              "mpl_toolkits", "mpl_toolkits.mplot3d", "skimage", "skimage.io", "skimage.transform", "cv2"]:
         sys.modules[m] = _Any(m)
+        sys.modules[m].__path__ = []
     np.float, np.int = float, int
     sys.dont_write_bytecode = True
     sys.path[:0] = [REF + "/skeleton_fitting/ik", REF + "/utils", REF, REF + "/optimize"]
