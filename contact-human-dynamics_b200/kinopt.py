@@ -467,3 +467,104 @@ def _global_positions(parents, off, x):
     T = np.tile(np.asarray(off)[None], (F, 1, 1))
     T[:, 0] = x[:, :3]
     return forward_kinematics(np.asarray(parents), rot_zyx(x[:, 3:].reshape(F, NJ, 3)), T)[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# File-level driver (src/optimize/kinematic_optimizer.py:30-224 optimize_2d_3d) and the Monocular-Total-Capture reader
+# ---------------------------------------------------------------------------------------------------------------------
+SMPL_SPINE_JOINTS = [3, 6, 9]                   # totalcap_utils.py:18
+# combined skeleton joint -> SMPL joint (-1: none), character_info_utils.py:222-251
+COMBINED_TO_SMPL = [0, 1, 4, 7, -1, -1, 10, 2, 5, 8, -1, -1, 11, 3, 6, 9, 12, 15, -1, -1, -1, -1, 16, 18, 20, 17, 19, 21]
+MTC_FOCAL = (2000.0, 2000.0)                    # kinematic_optimizer.py:22-28
+MTC_SIZE = (1920, 1080)
+
+
+def load_totalcap_results(path: str) -> dict:
+    """totalcap_utils.py:33-79: `tracked_results.json` of Monocular Total Capture -> root translation (F,3), BODY_25 joints
+    (F,25,3), SMPL joints (F,Js,3) and SMPL joint angles (F,Js,3 axis-angle)."""
+    import json
+    with open(path) as f:
+        frames = json.load(f)["totalcapResults"]
+    xyz = lambda d: [d["x"], d["y"], d["z"]]
+    return dict(root_trans=np.array([xyz(fr["trans"]) for fr in frames], dtype=np.float64),
+                joint3d=np.array([[xyz(j["pos"]) for j in fr["joints"]] for fr in frames], dtype=np.float64),
+                smpl_joint3d=np.array([[xyz(j["pos"]) for j in fr["SMPLJoints"]] for fr in frames], dtype=np.float64),
+                smpl_joint_angles=np.array([[xyz(j["rot"]) for j in fr["SMPLJoints"]] for fr in frames], dtype=np.float64))
+
+
+def combined_inputs(tc: dict):
+    """kinematic_optimizer.py:64-73: root-relative BODY_25 joints + the three SMPL spine joints, root translation moved into
+    `root_pos`, initial joint angles of the combined skeleton from the SMPL angles."""
+    root = tc["root_trans"] + tc["joint3d"][:, ROOT_IDX]
+    body = tc["joint3d"] - tc["joint3d"][:, ROOT_IDX:ROOT_IDX + 1]
+    smpl = tc["smpl_joint3d"] - tc["smpl_joint3d"][:, 0:1]
+    poses3D = np.concatenate([body, smpl[:, SMPL_SPINE_JOINTS]], axis=1)
+    ang = np.zeros((root.shape[0], NJ, 3))
+    for j, s in enumerate(COMBINED_TO_SMPL):
+        if s >= 0:
+            ang[:, j] = tc["smpl_joint_angles"][:, s]
+    return poses3D, root, ang
+
+
+def contacts_to_constraints(foot_contacts):
+    """(F,4) labels [L heel, L toe, R heel, R toe] -> (F,28) per-joint labels in body-25 order (kinematic_optimizer.py:106-116)."""
+    fc = np.asarray(foot_contacts)
+    vel = np.zeros((fc.shape[0], NJ))
+    vel[:, 19] = vel[:, 20] = fc[:, 1]
+    vel[:, 21] = fc[:, 0]
+    vel[:, 22] = vel[:, 23] = fc[:, 3]
+    vel[:, 24] = fc[:, 2]
+    return vel
+
+
+def constraints_to_contacts(vel):
+    """Refined per-joint labels -> (F,4) int [L heel, L toe, R heel, R toe] (kinematic_optimizer.py:183-204)."""
+    v = np.asarray(vel)
+    return np.stack([v[:, 21], np.logical_or(v[:, 19], v[:, 20]), v[:, 24], np.logical_or(v[:, 22], v[:, 23])], axis=1).astype(int)
+
+
+def optimize_2d_3d(input_path: str, skel_path: str, output_path: str, min_idx: int = 0, max_idx: int = 100, use_gt_floor: bool = False,
+                   device=None, frametime: float = 1.0 / 24.0):
+    """kinematic_optimizer.optimize_2d_3d: reads `<dir>/openpose_result/*.json`, `<dir>/tracked_results.json`,
+    `<dir>/foot_contacts.npy` next to `input_path`; writes `foot_contacts.npy` (refined, int), `floor_out.txt` and
+    `final_test.bvh` into `output_path`."""
+    import os
+    from . import contact
+    from .prepare import load_bvh
+    from .results import save_bvh
+    os.makedirs(output_path, exist_ok=True)
+    d = os.path.dirname(input_path)
+    op_dir, tc_path, fc_path = os.path.join(d, "openpose_result"), os.path.join(d, "tracked_results.json"), os.path.join(d, "foot_contacts.npy")
+    if not os.path.isdir(op_dir):
+        print("Could not find openpose results in " + op_dir + "!")
+        return None
+    if not os.path.isfile(tc_path):
+        print("Could not find total capture results!")
+        return None
+    if not os.path.isfile(fc_path):
+        print("Could not find foot contact labels!")
+        return None
+    kp = contact.load_keypoint_dir(op_dir)
+    poses3D, root_pos, ang = combined_inputs(load_totalcap_results(tc_path))
+    sl = slice(min_idx, max_idx)
+    n = len(range(*sl.indices(kp.shape[0])))
+    poses2D = np.concatenate([kp[sl, :, :2], np.zeros((n, 3, 2))], axis=1)
+    conf = np.concatenate([kp[sl, :, 2], np.zeros((n, 3))], axis=1)
+    fc = np.load(fc_path)
+    vel = contacts_to_constraints(fc[sl])
+    normal = point = None
+    if use_gt_floor:
+        with open(os.path.join(d, "floor_gt.txt")) as f:
+            normal = np.array([float(v) for v in f.readline().split()])
+            point = np.array([float(v) for v in f.readline().split()]) * 100.0
+    b = load_bvh(skel_path)
+    res = optimize_trajectory(poses2D, conf, poses3D[sl], root_pos[sl], ang[sl], b.parents, b.offsets, MTC_SIZE[0] / 2, MTC_SIZE[1] / 2,
+                              np.array(MTC_FOCAL), vel, plane_normal=normal, plane_point=point, device=device)
+    anim, new3d, proj, pn, pp, newvel, info = res
+    anim.names = list(b.names)
+    np.save(os.path.join(output_path, "foot_contacts"), constraints_to_contacts(newvel))
+    with open(os.path.join(output_path, "floor_out.txt"), "w") as f:
+        f.write("%s %s %s\n%s %s %s" % tuple(str(float(v)) for v in list(pn) + list(pp)))
+    save_bvh(os.path.join(output_path, "final_test.bvh"), anim, b.names, frametime)
+    print("Finished kinematic optimization!")
+    return res

@@ -167,6 +167,12 @@ class PhysBatch:
         self.sizes = sz  # n, m, nslots, Na, nb, w
         self.n_ee_max = max(p.n_ee for p in self.problems)
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     def close(self):
         if getattr(self, "h", None):
             self.L.chd_phys_batch_destroy(self.h)
@@ -303,6 +309,24 @@ class PhysBatch:
     def _chk(self, rc):
         if rc != 0:
             raise RuntimeError("libchd call failed with code %d" % rc)
+
+
+SOLUTION_FILES = ("sol_out_no_dynamics.txt", "sol_out_dynamics.txt", "sol_out_durations.txt")
+
+
+def write_outputs(out: dict, i: int, problem: PhysProblem, out_dir: str, n_ee_max: Optional[int] = None) -> None:
+    """The four files `phys_optim` leaves in --out_dir (phys_optim.cpp:63-153, 756-761) for sequence i of a `solve()` result."""
+    import os
+    from .io_formats import write_solution, write_success_log
+    n_ee = problem.n_ee
+    ne_max = n_ee_max if n_ee_max is not None else (out["samples"].shape[-1] - 6) // 7
+    nf = int(out["frames"][i])
+    # strip the padding columns of a mixed n_ee batch
+    cols = list(range(6)) + [6 + 3 * e + d for e in range(n_ee) for d in range(3)] + \
+        [6 + 3 * ne_max + 3 * e + d for e in range(n_ee) for d in range(3)] + [6 + 6 * ne_max + e for e in range(n_ee)]
+    for snap, name in enumerate(SOLUTION_FILES):
+        write_solution(os.path.join(out_dir, name), problem.dt, out["samples"][snap, i, :nf][:, cols], n_ee)
+    write_success_log(os.path.join(out_dir, "success_log.txt"), out["success"][i, 0], out["success"][i, 1])
 
 
 def master_row_slices(batch: PhysBatch, i: int, lay: Optional[dict] = None):

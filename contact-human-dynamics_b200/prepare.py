@@ -88,6 +88,22 @@ def ybot_info() -> "CharacterInfo":
 
 CHARACTERS = {"combined": combined_info, "ybot": ybot_info}
 
+# A 28-joint template with the `combined` joint numbering (own proportions, cm, y pointing down like the camera frame): used
+# by the synthetic clips of the tests / plumbing configuration; the reference ships skeleton_fitting/combined_body_25.bvh.
+COMBINED_NAMES = ["Hips", "LHip", "LKnee", "LAnkle", "LHeel", "LBigToe", "LSmallToe", "RHip", "RKnee", "RAnkle", "RHeel", "RBigToe",
+                  "RSmallToe", "Spine", "Spine1", "Spine2", "Neck", "Nose", "LEye", "LEar", "REye", "REar", "LShoulder", "LElbow", "LWrist",
+                  "RShoulder", "RElbow", "RWrist"]
+COMBINED_PARENTS = [-1, 0, 1, 2, 3, 3, 3, 0, 7, 8, 9, 9, 9, 0, 13, 14, 15, 16, 17, 18, 17, 20, 16, 22, 23, 16, 25, 26]
+COMBINED_OFFSETS = [[0, 0, 0], [9.5, 3, 0.5], [0.4, 41, 0.8], [0.2, 40, -1.2], [0.3, 7.5, -5.5], [1.5, 8, 13.5], [-3.5, 8.2, 11],
+                    [-9.5, 3, 0.5], [-0.4, 41, 0.8], [-0.2, 40, -1.2], [-0.3, 7.5, -5.5], [-1.5, 8, 13.5], [3.5, 8.2, 11],
+                    [0, -11, -1], [0, -13, 0.5], [0, -13, 0.5], [0, -15, 1], [0, -12, 9], [3, -3, -2], [5, 1, -8], [-3, -3, -2], [-5, 1, -8],
+                    [17, 1, -1], [2, 27, 0], [1, 25, 2], [-17, 1, -1], [-2, 27, 0], [-1, 25, 2]]
+
+
+def write_combined_template(path: str):
+    """Rest pose of the template as a one-frame BVH (what `--skel_path` of the kinematic optimiser takes)."""
+    write_bvh(path, COMBINED_NAMES, COMBINED_PARENTS, COMBINED_OFFSETS, np.zeros((1, 3 + 3 * len(COMBINED_NAMES))), 1.0 / 30.0, order="ZXY")
+
 
 @dataclass
 class Bvh:

@@ -228,3 +228,77 @@ def make_batch(batch: int, n_frames: int = 120, n_ee: int = 2, seed0: int = 0, d
                fps: float = 30.0) -> List[PhysProblem]:
     """Seeds seed0 .. seed0+batch-1, one per sequence."""
     return [make_problem(seed0 + i, n_frames, n_ee, fps, dense) for i in range(batch)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# A synthetic video directory for the pipeline on either side of phys-optim (no capture data ships with the reference):
+# OpenPose BODY_25 JSON files, a Monocular-Total-Capture `tracked_results.json`, contact labels, and the skeleton template.
+# ---------------------------------------------------------------------------------------------------------------------
+def write_mocap_clip(video_dir: str, n_frames: int = 48, seed: int = 0, fps: float = 30.0, noise_px: float = 1.0, noise_cm: float = 0.5):
+    """Walking clip in the MTC camera frame (x right, y down, z forward, cm; focal 2000 px, 1920 x 1080): feet planted during
+    stance, joint angles from an IK fit of the `combined` template.  Writes `<video_dir>/openpose_result/*_keypoints.json`,
+    `tracked_results.json`, `foot_contacts.npy`, `skeleton.bvh`; returns the ground truth (dict)."""
+    import json
+    import os
+    from . import kinopt, prepare, results
+    rng = np.random.default_rng(seed)
+    F, J = n_frames, len(prepare.COMBINED_NAMES)
+    t = np.arange(F) / fps
+    T_step, speed, floor_y, z0 = rng.uniform(0.9, 1.0), rng.uniform(60.0, 75.0), 92.0, rng.uniform(380.0, 420.0)
+    step = speed * T_step
+    x0 = -60.0 + rng.uniform(-10, 10)
+
+    def foot(offset, z_lat):
+        ph = t / T_step + offset
+        k, s = np.floor(ph), ph - np.floor(ph)
+        stance = s < 0.6
+        u = np.clip((s - 0.6) / 0.4, 0.0, 1.0)
+        sm = u * u * (3.0 - 2.0 * u)
+        x = x0 + (k + 0.3 + np.where(stance, 0.0, sm)) * step - offset * step      # lands ahead of the hips, leaves behind them
+        y = floor_y - np.where(stance, 0.0, 9.0 * np.sin(np.pi * u))
+        toe = np.stack([x, y, np.full(F, z0 + z_lat)], axis=1)
+        return toe, toe - np.array([17.0, 0.0, 0.0]), stance
+
+    l_toe, l_heel, l_st = foot(0.0, -9.5)
+    r_toe, r_heel, r_st = foot(0.5, +9.5)
+    root = np.stack([x0 + speed * t - 6.0, floor_y - 82.0 - 1.5 * np.sin(4 * np.pi * t / T_step), np.full(F, z0)], axis=1)
+    off = np.asarray(prepare.COMBINED_OFFSETS, dtype=np.float64)
+    R0 = np.tile(np.eye(3), (F, J, 1, 1))
+    R0[:, 0] = results.rot_zyx(np.array([0.0, np.pi / 2, 0.0]))          # template faces +z, the walk goes along +x
+    P0 = np.tile(off[None], (F, 1, 1))
+    P0[:, 0] = root
+    anim = results.SkelAnim(list(prepare.COMBINED_NAMES), np.array(prepare.COMBINED_PARENTS), off, R0, P0)
+    targets = {4: l_heel, 5: l_toe, 10: r_heel, 11: r_toe, 16: root + np.array([4.0, -51.0, 0.0])}
+    anim = results.ik_solve(anim, targets, iterations=80, damping=2.0, smoothness=0.0, translate=False)
+    gp = anim.global_positions()                                                            # (F, 28, 3) absolute, skeleton order
+    body = gp[:, kinopt.BACKWARD]                                                           # body-25 order (+3 spine)
+    fc = np.stack([l_st, l_st, r_st, r_st], axis=1).astype(np.int64)                        # L heel, L toe, R heel, R toe
+    os.makedirs(os.path.join(video_dir, "openpose_result"), exist_ok=True)
+    name = os.path.basename(os.path.normpath(video_dir))
+    kp2d = body[:, :25, :2] / body[:, :25, 2:3] * 2000.0 + np.array([960.0, 540.0]) + rng.normal(0, noise_px, (F, 25, 2))
+    conf = rng.uniform(0.4, 1.0, (F, 25))
+    for f in range(F):
+        doc = {"version": 1.3, "people": [{"person_id": [-1], "pose_keypoints_2d": [float(v) for v in np.concatenate([kp2d[f], conf[f, :, None]], axis=1).reshape(-1)]}]}
+        with open(os.path.join(video_dir, "openpose_result", "%s_%012d_keypoints.json" % (name, f)), "w") as fh:
+            json.dump(doc, fh)
+    # MTC results: BODY_25 joints relative to the root translation, 22 SMPL joints (root + spine positions, joint angles)
+    Rl = anim.rotations
+    ang = np.arccos(np.clip((np.trace(Rl, axis1=-2, axis2=-1) - 1.0) / 2.0, -1.0, 1.0))
+    ax = np.stack([Rl[..., 2, 1] - Rl[..., 1, 2], Rl[..., 0, 2] - Rl[..., 2, 0], Rl[..., 1, 0] - Rl[..., 0, 1]], -1)
+    aa = -(ax / (np.linalg.norm(ax, axis=-1, keepdims=True) + 1e-12)) * ang[..., None] + rng.normal(0, 0.02, (F, J, 3))
+    rel = body[:, :25] - root[:, None] + rng.normal(0, noise_cm, (F, 25, 3))
+    rel[:, kinopt.ROOT_IDX] = 0.0
+    smpl_pos, smpl_rot = np.zeros((F, 22, 3)), np.zeros((F, 22, 3))
+    for j, s in enumerate(kinopt.COMBINED_TO_SMPL):
+        if s >= 0:
+            smpl_pos[:, s] = gp[:, j] - root + rng.normal(0, noise_cm, (F, 3))
+            smpl_rot[:, s] = aa[:, j]
+    smpl_pos[:, 0] = 0.0
+    xyz = lambda v: {"x": float(v[0]), "y": float(v[1]), "z": float(v[2])}
+    frames = [{"trans": xyz(root[f]), "joints": [{"pos": xyz(rel[f, j])} for j in range(25)],
+               "SMPLJoints": [{"pos": xyz(smpl_pos[f, s]), "rot": xyz(smpl_rot[f, s])} for s in range(22)], "bodyCoeffs": [], "faceCoeffs": []} for f in range(F)]
+    with open(os.path.join(video_dir, "tracked_results.json"), "w") as fh:
+        json.dump({"totalcapResults": frames}, fh)
+    np.save(os.path.join(video_dir, "foot_contacts.npy"), fc)
+    prepare.write_combined_template(os.path.join(video_dir, "skeleton.bvh"))
+    return dict(root=root, joints=gp, contacts=fc, floor_y=floor_y, euler=None, fps=fps)

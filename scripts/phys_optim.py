@@ -60,18 +60,8 @@ def main(argv=None):
         return
     batch = chd.phys.PhysBatch(problems, weights=weights)
     out = batch.solve()
-    names = ["sol_out_no_dynamics.txt", "sol_out_dynamics.txt", "sol_out_durations.txt"]
     for i, (p, od) in enumerate(zip(problems, out_dirs)):
-        nf = int(out["frames"][i])
-        n_ee = p.n_ee
-        for snap, name in enumerate(names):
-            s = out["samples"][snap, i, :nf]
-            # strip the padding columns of a mixed n_ee batch
-            ne_max = batch.n_ee_max
-            cols = list(range(6)) + [6 + 3 * e + d for e in range(n_ee) for d in range(3)] + \
-                [6 + 3 * ne_max + 3 * e + d for e in range(n_ee) for d in range(3)] + [6 + 6 * ne_max + e for e in range(n_ee)]
-            chd.io_formats.write_solution(os.path.join(od, name), p.dt, s[:, cols], n_ee)
-        chd.io_formats.write_success_log(os.path.join(od, "success_log.txt"), out["success"][i, 0], out["success"][i, 1])
+        chd.phys.write_outputs(out, i, p, od, batch.n_ee_max)
         print("[%d] stages status %s iterations %s -> %s" % (i, out["stage_status"][:, i].tolist(), out["stage_iters"][:, i].tolist(), od))
 
 

@@ -98,3 +98,58 @@ def test_bvh_clip_through_prepare_input(chd, tmp_path):
         assert all(np.isfinite(np.asarray(v, float)).all() for v in r[key].values() if isinstance(v, np.ndarray))
     # the kinematic stage tracks the prepared COM (z up, metres)
     assert np.abs(r["no_dynamics"]["base_lin"] - p.base_lin).mean() < 0.1
+
+
+def test_run_phys_mocap_whole_chain(chd, tmp_path):
+    """The reference's driver scripts/run_phys_mocap.py end to end on two synthetic video directories (configs[0] `single
+    example_data clip (plumbing)`): OpenPose JSON + MTC json + contact labels -> kinematic initialisation
+    (torch on the GPU) -> phys_optim_in_* -> ONE batched staged solve (libchd) -> sol_out_* -> IK back onto the skeleton ->
+    BVH files."""
+    data = tmp_path / "data"
+    gts = {}
+    for name, F, seed in (("clipA", 40, 1), ("clipB", 48, 2)):
+        gts[name] = (F, chd.synth.write_mocap_clip(str(data / name), F, seed=seed))
+    skel = str(data / "clipA" / "skeleton.bvh")
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "run_phys_mocap.py"), "--data", str(data), "--character", "combined",
+                           "--skel_path", skel, "--fps", "30"])
+    for name, (F, gt) in gts.items():
+        vd = data / name
+        for f in ("foot_contacts.npy", "floor_out.txt", "final_test.bvh", "combined_out.bvh"):
+            assert (vd / "kinematic_results" / f).exists(), f
+        for f in ("skel_info.txt", "motion_info.txt", "terrain_info.txt", "contact_info.txt"):
+            assert (vd / "phys_optim_in_combined" / f).exists(), f
+        out = vd / "phys_optim_out_combined"
+        log = open(out / "success_log.txt").read().split()
+        assert log[0] == "dynamics" and log[2] == "durations" and log[1] in "01" and log[3] in "01"
+        for tag in ("no_dynamics", "dynamics", "durations"):
+            r = chd.results.load_towr_results(str(out / ("sol_out_%s.txt" % tag)))
+            assert r.num_feet == 4 and r.base_pos.shape == (F, 3) and np.isfinite(r.feet_pos).all()
+            b = chd.prepare.load_bvh(str(out / ("%s_combined_%s.bvh" % (name, tag))))
+            assert b.n_frames == F and len(b.names) == 28
+            # the applied skeleton follows the optimised COM track: root within the body's extent of it (cm, BVH frame)
+            R, T = chd.prepare.local_transforms(b)
+            gp, _ = chd.prepare.forward_kinematics(b.parents, R, T)
+            assert np.linalg.norm(gp[:, 0] - r.base_pos * 100.0, axis=1).max() < 40.0
+            # the toes were pulled onto the optimised foot trajectories
+            assert np.linalg.norm(gp[:, 5] - r.feet_pos[:, 0] * 100.0, axis=1).mean() < 3.0
+        # kinematic stage of the physics solve stays near the kinematic initialisation (metres)
+        r0 = chd.results.load_towr_results(str(out / "sol_out_no_dynamics.txt"))
+        p = chd.io_formats.read_phys_inputs(str(vd / "phys_optim_in_combined"), F)
+        com_bvh = -p.base_lin[:, [0, 2, 1]]
+        assert np.abs(r0.base_pos - com_bvh).mean() < 0.05
+
+
+def test_torch_batched_solvers_same_on_gpu_and_cpu(chd, tmp_path):
+    """The kinematic optimiser and the IK are torch-batched over the frames: same numbers on cuda:0 and on the host."""
+    import torch
+    assert torch.cuda.is_available()
+    vd = str(tmp_path / "w")
+    chd.synth.write_mocap_clip(vd, 24, seed=5)
+    outs = []
+    for dev in (None, "cuda:0"):
+        res = chd.kinopt.optimize_2d_3d(os.path.join(vd, "w.mp4"), os.path.join(vd, "skeleton.bvh"), str(tmp_path / ("k_%s" % dev)), 0, 24, device=dev)
+        outs.append(res)
+    c0, c1 = outs[0][-1]["stage2"]["cost"], outs[1][-1]["stage2"]["cost"]
+    assert abs(c0 - c1) < 1e-3 * c0
+    assert np.linalg.norm(outs[0][1] - outs[1][1], axis=-1).max() < 0.5        # cm; 100 LM evaluations amplify rounding differences
+    np.testing.assert_allclose(outs[0][3], outs[1][3], atol=1e-3)              # floor normal
