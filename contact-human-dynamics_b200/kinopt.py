@@ -275,12 +275,30 @@ class _Model:
         return cost, H, g
 
 
-def _banded_cholesky_solve(t, H, g, lam):
+DENSE_MAX_UNKNOWNS = 24000      # 4.6 GB of fp64 at the limit (275 frames)
+
+
+def _banded_cholesky_solve(t, H, g, lam, dense=None):
     """Solves (H + lam * diag(H)) s = g for the symmetric block-pentadiagonal H = (diag blocks, first and second lower block
     bands: H[1][f] = block (f+1, f), H[2][f] = block (f+2, f)).  One sweep of block Cholesky, F steps of 87 x 87 work."""
     D, B1, B2 = H
     F, n = D.shape[0], D.shape[1]
     Dd = D + lam * t.diag_embed(t.diagonal(D, dim1=1, dim2=2).clamp_min(1e-12))
+    if dense is None:
+        # on the GPU the sweep below is F dependent steps of a few tiny kernels each (launch bound: ~0.2 s per solve at 120
+        # frames); one dense fp64 Cholesky of the (87 F)^2 matrix is far faster there as long as it fits comfortably
+        dense = D.is_cuda and F * n <= DENSE_MAX_UNKNOWNS
+    if dense:
+        A = t.zeros(F * n, F * n, dtype=D.dtype, device=D.device)
+        A4 = A.view(F, n, F, n)
+        i0 = t.arange(F, device=D.device)
+        A4[i0, :, i0, :] = Dd
+        if F > 1:
+            A4[i0[1:], :, i0[:-1], :] = B1
+        if F > 2:
+            A4[i0[2:], :, i0[:-2], :] = B2
+        L = t.linalg.cholesky(A)                       # reads the lower triangle only
+        return t.cholesky_solve(g.reshape(-1, 1), L).reshape(F, n)
     L0, L1, L2 = [None] * F, [None] * F, [None] * F                               # L1[f] = L(f+1, f), L2[f] = L(f+2, f)
     for f in range(F):
         A = Dd[f].clone()

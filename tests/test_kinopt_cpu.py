@@ -93,6 +93,8 @@ def test_normal_equations_and_banded_solver(chd, data):
     s = ko._banded_cholesky_solve(torch, H, g, lam).reshape(-1).numpy()
     A = Hd + lam * np.diag(np.diag(Hd))
     np.testing.assert_allclose(s, np.linalg.solve(A, g.reshape(-1).numpy()), rtol=1e-6, atol=1e-9)
+    sd = ko._banded_cholesky_solve(torch, H, g, lam, dense=True).reshape(-1).numpy()      # the GPU path: one dense factorisation
+    np.testing.assert_allclose(sd, s, rtol=1e-8, atol=1e-10)
 
 
 def test_objective_at_reference_solution_and_own_run(chd, data):
