@@ -580,8 +580,22 @@ int chd_phys_solve_stage(chd_phys_batch* b, int32_t stage, int32_t max_iter, int
 
 int chd_phys_sample_device(chd_phys_batch* b, double* out_device, void* stream) {
   if (!b || !out_device || b->host_only) return -1;
-  Timer t(b, KT_SAMPLE);
-  chd_k_sample<<<b->hb.B, 128, 0, stream ? (cudaStream_t)stream : b->stream>>>(b->D, out_device, b->d_frames);
+  cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+  if (st == b->stream) {
+    Timer t(b, KT_SAMPLE);
+    chd_k_sample<<<b->hb.B, 128, 0, st>>>(b->D, out_device, b->d_frames);
+    return 0;
+  }
+  // caller's stream: order the launch behind everything pending on the batch's own stream (reset / upload copies, the
+  // solve) and make the batch's stream wait for it in turn (it writes d_frames and reads x)
+  cudaEvent_t ev;
+  CHD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CHD_CUDA(cudaEventRecord(ev, b->stream));
+  CHD_CUDA(cudaStreamWaitEvent(st, ev, 0));
+  chd_k_sample<<<b->hb.B, 128, 0, st>>>(b->D, out_device, b->d_frames);
+  CHD_CUDA(cudaEventRecord(ev, st));
+  CHD_CUDA(cudaStreamWaitEvent(b->stream, ev, 0));
+  CHD_CUDA(cudaEventDestroy(ev));
   return 0;
 }
 
