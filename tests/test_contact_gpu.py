@@ -71,3 +71,27 @@ def test_device_preprocessing_matches_reference_golden(chd):
     det, _ = net.detect(raw)
     for i, n in enumerate(names):
         np.testing.assert_array_equal(det[i], g["contacts_" + n])
+
+
+def test_trained_weights_drive_cuda_inference(chd):
+    """Training (chd.train, torch on cuda:0) -> state_dict -> chd_contact_create: the CUDA inference path reproduces the
+    eval-mode forward of the trained parameters (running statistics included) on the golden clips."""
+    import torch
+    T = chd.train
+    g = dict(np.load(os.path.join(HERE, "golden", "contact", "contact_golden.npz")))
+    names = [str(n) for n in g["names"]]
+    frames = np.stack([g["proc_" + n] for n in names])
+    tr = T.Trainer(seed=4, lr=1e-3, device="cuda")
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x = torch.as_tensor(rng.normal(0, 0.5, (64, 9, 13, 3)).astype(np.float32), device="cuda")
+        y = torch.as_tensor((rng.uniform(size=(64, 5, 4)) < 0.5).astype(np.float32), device="cuda")
+        tr.step(x, y)
+    sd = tr.state_dict_numpy()
+    assert int(sd["model.1.num_batches_tracked"]) == 20
+    net = chd.contact.ContactNet(sd)
+    labels, logits, mabs = net.forward(frames, g["seq_lens"].astype(np.int32), want_logits=True)
+    win = torch.as_tensor(g["windows"].reshape(-1, 9, 13, 3), device="cuda")
+    with torch.no_grad():
+        ref = T.forward(tr.sd, win, False).cpu().numpy().reshape(logits.shape)
+    np.testing.assert_allclose(logits, ref, rtol=0, atol=5e-5 * max(1.0, float(np.abs(ref).max())))
