@@ -96,3 +96,17 @@ def test_save_bvh_round_trip(chd, tmp_path):
     np.testing.assert_allclose(R, an.rotations, atol=5e-8)         # six decimals of a degree
     np.testing.assert_allclose(T[:, 0], an.positions[:, 0], atol=1e-6)
     assert b.channels[0][3:] == ["Zrotation", "Yrotation", "Xrotation"]
+
+
+def test_oracle_euler_convention_is_the_reference_consumers(chd):
+    """An anchor outside our own reading of TOWR: the reference's consumer of `base_ang` (towr_utils.load_results:115,
+    `Quaternions.from_euler(order='xyz', world=True)`, executed by the golden generator) assigns the same rotation to the
+    written angles as the oracle's EulerConverter restatement does (R = Rz Ry Rx; tests/test_oracle_cpu.py ties that to the
+    oracle's `euler()`), so the orientation the solver optimises is the orientation the pipeline applies to the skeleton."""
+    from scipy.spatial.transform import Rotation
+    d = os.path.join(G, "combined")
+    g = np.load(d + "/results.npz")
+    ang = chd.io_formats.read_solution(d + "/sol_out.txt")["base_ang_deg"]            # degrees, as phys_optim writes them
+    R = Rotation.from_euler("xyz", np.radians(ang)).as_matrix()                   # extrinsic xyz = Rz Ry Rx, the oracle's convention
+    C = chd.prepare.C_BVH_TO_TOWR
+    np.testing.assert_allclose(C @ R @ C.T, g["base_R"], atol=1e-9)
