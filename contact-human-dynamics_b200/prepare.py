@@ -43,6 +43,8 @@ class CharacterInfo:
     mass: float = MALE_MASS
     heel_inds: Optional[Tuple[int, int]] = None   # skeletons that already carry heel joints
     upper_body_joints: Optional[List[int]] = None  # incl. the root: what apply_results pins to the optimised COM
+    to_combined: Optional[List[int]] = None        # character joint -> joint of the `combined` skeleton (-1: none), re-targeting
+    ik_blacklist: Optional[List[int]] = None       # mapped joints that are not IK targets when re-targeting
 
     @property
     def hips(self):
@@ -83,7 +85,10 @@ def ybot_info() -> "CharacterInfo":
     return CharacterInfo(left_leg_chain=[62, 63, 64, 65], right_leg_chain=[57, 58, 59, 60],
                          segment_to_joints=_segments([5], [3], [2], [1], [10, 11], [11, 12], range(12, 33), [62, 63], [63, 64], [64, 65, 66],
                                                      [34, 35], [35, 36], range(36, 57), [57, 58], [58, 59], [59, 60, 61]),
-                         segment_mass_percent=dict(MASS_PERCENT_MALE), upper_body_joints=list(range(0, 57)))
+                         segment_mass_percent=dict(MASS_PERCENT_MALE), upper_body_joints=list(range(0, 57)),
+                         to_combined=[0, 13, 14, 15, 16, -1, -1, 18, 20, -1, 22, 23, 24] + [-1] * 21 + [25, 26, 27] + [-1] * 20 +
+                                     [7, 8, 9, 11, -1, 1, 2, 3, 5, -1],             # character_info_utils.py:319-388
+                         ik_blacklist=[10, 11, 12, 34, 35, 36])
 
 
 CHARACTERS = {"combined": combined_info, "ybot": ybot_info}

@@ -253,3 +253,66 @@ def save_bvh(path: str, anim: SkelAnim, names: Optional[Sequence[str]] = None, f
     F, J = e.shape[:2]
     rows = np.concatenate([anim.positions[:, 0], e[:, :, [2, 1, 0]].reshape(F, 3 * J)], axis=1)
     write_bvh(path, names, anim.parents, anim.offsets, rows, frametime, order="ZYX")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Re-targeting of the kinematic result (28-joint `combined` skeleton) to a character skeleton
+# (src/skeleton_fitting/combined_to_mixamo.py:38-134), between kinematic_optimizer.py and towr_utils.py in the pipeline.
+# ---------------------------------------------------------------------------------------------------------------------
+COMBINED_FOOT_INDS = [4, 5, 6, 10, 11, 12]      # character_info_utils.py:196-199
+COMBINED_ANKLE_INDS = [3, 9]
+
+
+def _softmin(x, softness=0.5):
+    """combined_to_mixamo.py:30-36 over axis 0: -(max(-x) + log(softness + exp(min(-x) - max(-x))))."""
+    nx = -np.asarray(x, dtype=np.float64)
+    return -(nx.max() + np.log(softness + np.exp(nx.min() - nx.max())))
+
+
+def retarget(src_bvh: str, skel_bvh: str, info: CharacterInfo, out_bvh: Optional[str] = None, device=None, iterations: int = 200):
+    """combined_to_mixamo.retarget: scales the source joint positions by the ratio of the hip heights (floor at 0 through a
+    soft minimum of the foot heights), initialises the character's angles from the mapped source Euler angles, runs the
+    damped least-squares IK (translating joints, 200 iterations, damping 7) towards the mapped joints, restores the bone
+    offsets and corrects the root height by the median ankle difference.  Returns the SkelAnim (and saves it if asked)."""
+    sk = load_bvh(skel_bvh)
+    J = len(sk.names)
+    Rk, Tk = local_transforms(sk)
+    skel_targets = forward_kinematics(sk.parents, np.tile(np.eye(3), (Tk.shape[0], J, 1, 1)), Tk)[0]      # rotations zeroed
+    foot = [info.ankles[0], info.toes[0], info.ankles[1], info.toes[1]]
+    fh = np.minimum(skel_targets[:, foot[:2], 1], skel_targets[:, foot[2:], 1]).min(axis=1)
+    skel_targets[:, :, 1] -= _softmin(fh)
+    skel_height = np.abs(np.amax(skel_targets[:, 0, 1]) - np.amin(skel_targets[:, foot, 1], axis=1)).max()
+    src = load_bvh(src_bvh)
+    Rs, Ts = local_transforms(src)
+    at = forward_kinematics(src.parents, Rs, Ts)[0]
+    F = at.shape[0]
+    at[:, :, 1] = -at[:, :, 1]                                                   # y points down in the source: flip to measure heights
+    fl, fr = COMBINED_FOOT_INDS[:3], COMBINED_FOOT_INDS[3:]
+    src_floor = _softmin(np.minimum(at[:, fl, 1], at[:, fr, 1]).min(axis=1))
+    at[:, :, 1] -= src_floor
+    anim_height = np.abs(np.amax(at[:, 0, 1]) - np.amin(at[:, COMBINED_FOOT_INDS, 1], axis=1)).max()
+    at[:, :, 1] = -at[:, :, 1]
+    ratio = skel_height / anim_height
+    targets = at * ratio
+    targets[:, :, [0, 2]] -= (targets[:, 0, [0, 2]] - at[:, 0, [0, 2]])[:, None, :]      # hip translation in x / z is not scaled
+    mp = info.to_combined
+    tm = {i: targets[:, mp[i]] for i in range(J) if mp[i] > -1 and i not in info.ik_blacklist}
+    es = euler_zyx_from_matrix(Rs)
+    ref = np.zeros((F, J, 3))
+    for i in range(J):
+        if mp[i] > -1:
+            ref[:, i] = np.fmod(es[:, mp[i]] * 180 / 3.1415, 180) * 3.1415 / 180     # the reference's constants
+    P0 = np.tile(sk.offsets[None], (F, 1, 1))
+    P0[:, 0] = targets[:, 0]
+    anim = SkelAnim(list(sk.names), sk.parents.copy(), sk.offsets.copy(), rot_zyx(ref), P0)
+    anim = ik_solve(anim, tm, iterations=iterations, smoothness=0.0, damping=7.0, translate=True, device=device)
+    anim.positions[:, 1:] = sk.offsets[None, 1:]
+    ank = targets[:, COMBINED_ANKLE_INDS, 1] - anim.global_positions()[:, info.ankles, 1]
+    anim.positions[:, 0, 1] += np.median(ank)
+    anim.positions[:, 0, 1] -= src_floor
+    if out_bvh:
+        d = os.path.dirname(out_bvh)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        save_bvh(out_bvh, anim, anim.names)
+    return anim

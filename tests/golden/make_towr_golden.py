@@ -169,5 +169,36 @@ def main():
         print(case, "done", anim.rotations.qs.shape)
 
 
+def retarget_golden():
+    """combined_to_mixamo.retarget of the reference on the `combined` golden clip, towards the synthetic 67-joint skeleton (the
+    reference hard-codes `<its dir>/<character>.bvh`: the loader is pointed at our skeleton file instead; h5py is stubbed)."""
+    tu = import_reference()
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    sys.path.insert(0, REF + "/skeleton_fitting")
+    from chd import prepare
+    import combined_to_mixamo as ctm
+    import Animation
+    d = os.path.join(OUT, "retarget")
+    os.makedirs(d, exist_ok=True)
+    names, parents, off, key = ybot_skeleton()
+    rest = np.zeros((1, 3 + 3 * len(names)))
+    rest[0, 1] = -97.0
+    skel = os.path.join(d, "ybot_skel.bvh")
+    prepare.write_bvh(skel, names, parents, off, rest, 1.0 / 30.0, order="ZXY")
+    orig = ctm.BVH.load
+    ctm.BVH.load = lambda path, *a, **k: orig(skel if os.path.basename(path) == "ybot.bvh" else path, *a, **k)
+    ctm.args = types.SimpleNamespace(character="ybot", src_bvh=os.path.join(OUT, "combined", "anim.bvh"))
+    out = os.path.join(d, "ref_out.bvh")
+    ctm.retarget(ctm.args.src_bvh, "ybot", out)
+    ctm.BVH.load = orig
+    anim, _, _ = orig(out)
+    np.savez(os.path.join(d, "retarget.npz"), rot_q=anim.rotations.qs, pos=anim.positions, gpos=Animation.positions_global(anim))
+    os.remove(out)
+    print("retarget done", anim.rotations.qs.shape)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "retarget":
+        retarget_golden()
+    else:
+        main()

@@ -110,3 +110,14 @@ def test_oracle_euler_convention_is_the_reference_consumers(chd):
     R = Rotation.from_euler("xyz", np.radians(ang)).as_matrix()                   # extrinsic xyz = Rz Ry Rx, the oracle's convention
     C = chd.prepare.C_BVH_TO_TOWR
     np.testing.assert_allclose(C @ R @ C.T, g["base_R"], atol=1e-9)
+
+
+def test_retarget_matches_reference(chd):
+    """combined_to_mixamo.retarget of the reference (golden: run on the `combined` clip towards the synthetic 67-joint
+    skeleton, result read back from the BVH it saved: six decimals) vs chd.results.retarget."""
+    g = np.load(os.path.join(G, "retarget", "retarget.npz"))
+    a = chd.results.retarget(os.path.join(G, "combined", "anim.bvh"), os.path.join(G, "retarget", "ybot_skel.bvh"), chd.prepare.ybot_info())
+    np.testing.assert_allclose(a.rotations, qmat(g["rot_q"]), atol=5e-7)
+    np.testing.assert_allclose(a.positions, g["pos"], atol=2e-6)
+    np.testing.assert_allclose(a.global_positions(), g["gpos"], atol=2e-5)
+    np.testing.assert_allclose(a.positions[:, 1:], np.tile(a.offsets[None, 1:], (a.positions.shape[0], 1, 1)), atol=0)   # bones restored
