@@ -51,6 +51,33 @@ def test_kinematic_driver_to_phys_inputs(chd, tmp_path):
         assert abs(sum(q.ee_durations[e]) - (F - 1) / 30.0) < 1e-9
 
 
+def test_retargeted_character_to_phys_inputs(chd, tmp_path):
+    """run_phys_mocap.py:117-153 for a Mixamo-style character: kinematic result -> re-targeting -> prepare_input with the
+    character's tables (heel joints added on the fly)."""
+    F = 24
+    vd = str(tmp_path / "walk")
+    chd.synth.write_mocap_clip(vd, F, seed=3)
+    kin = os.path.join(vd, "kinematic_results")
+    chd.kinopt.optimize_2d_3d(os.path.join(vd, "walk.mp4"), os.path.join(vd, "skeleton.bvh"), kin, 0, F)
+    skel = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "towr", "retarget", "ybot_skel.bvh")
+    info = chd.prepare.ybot_info()
+    out = os.path.join(kin, "ybot_out.bvh")
+    anim = chd.results.retarget(os.path.join(kin, "final_test.bvh"), skel, info, out, iterations=60)
+    assert len(anim.names) == 67 and anim.rotations.shape[0] == F
+    src = chd.prepare.load_bvh(os.path.join(kin, "final_test.bvh"))
+    gs = chd.prepare.forward_kinematics(src.parents, *chd.prepare.local_transforms(src))[0]
+    ga = anim.global_positions()
+    # the character walks where the source walks (x / z of the hips are not scaled) and its feet follow the source's feet
+    np.testing.assert_allclose(ga[:, 0, [0, 2]], gs[:, 0, [0, 2]], atol=2.0)       # cm: the IK may shift the root a little
+    assert np.linalg.norm(ga[:, 65] - ga[:, 60], axis=1).max() < 80.0
+    pin = str(tmp_path / "phys_in_ybot")
+    p = chd.prepare.prepare_input(out, os.path.join(kin, "floor_out.txt"), os.path.join(kin, "foot_contacts.npy"), pin, info, 0, F, 1.0 / 30.0, False)
+    q = chd.io_formats.read_phys_inputs(pin, F)
+    assert q.n_ee == 4 and q.n_frames == F and 0.7 < q.max_leg_length < 1.2
+    com_h = (q.base_lin - q.floor_point) @ q.floor_normal
+    assert 0.6 < com_h.min() and com_h.max() < 1.4
+
+
 def test_contact_label_mapping_round_trip(chd):
     rng = np.random.default_rng(0)
     fc = rng.integers(0, 2, (20, 4))
