@@ -153,3 +153,25 @@ def test_torch_batched_solvers_same_on_gpu_and_cpu(chd, tmp_path):
     assert abs(c0 - c1) < 1e-3 * c0
     assert np.linalg.norm(outs[0][1] - outs[1][1], axis=-1).max() < 0.5        # cm; 100 LM evaluations amplify rounding differences
     np.testing.assert_allclose(outs[0][3], outs[1][3], atol=1e-3)              # floor normal
+
+
+def test_run_phys_mocap_retargeted_character(chd, tmp_path):
+    """Same chain with `--character ybot`: re-targeting onto a 67-joint skeleton, heel joints added for the physics inputs and
+    the IK, removed again before the BVH is saved (run_phys_mocap.py:117-201, towr_utils.py:972-975)."""
+    data = tmp_path / "data"
+    F = 36
+    chd.synth.write_mocap_clip(str(data / "clipC"), F, seed=4)
+    skel = str(data / "clipC" / "skeleton.bvh")
+    ybot = os.path.join(ROOT, "tests", "golden", "towr", "retarget", "ybot_skel.bvh")
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "run_phys_mocap.py"), "--data", str(data), "--character", "ybot",
+                           "--skel_path", skel, "--character_skel", ybot, "--fps", "30"])
+    vd = data / "clipC"
+    assert (vd / "kinematic_results" / "ybot_out.bvh").exists()
+    assert chd.io_formats.read_phys_inputs(str(vd / "phys_optim_in_ybot"), F).n_ee == 4
+    out = vd / "phys_optim_out_ybot"
+    for tag in ("no_dynamics", "dynamics", "durations"):
+        r = chd.results.load_towr_results(str(out / ("sol_out_%s.txt" % tag)))
+        b = chd.prepare.load_bvh(str(out / ("clipC_ybot_%s.bvh" % tag)))
+        assert b.n_frames == F and len(b.names) == 67                      # heels removed again
+        gp, _ = chd.prepare.forward_kinematics(b.parents, *chd.prepare.local_transforms(b))
+        assert np.linalg.norm(gp[:, 65] - r.feet_pos[:, 0] * 100.0, axis=1).mean() < 3.0      # left toe on its optimised track
