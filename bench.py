@@ -382,15 +382,20 @@ def main():
             "e2e": {"value": M["N"] * frames * args.steps / e2e_total, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "includes": "layout build, H2D, staged solve, device sampling, the NCCL gather (N>1), D2H"},
             "gpu_launches": int(M["launches"]),
-            "roofline": {"bound": "hbm", "kernel": "chd_k_kkt", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": launch_bytes, "peak_source": peak_src,
-                         "note": "fp64-FMA / latency bound kernel (DESIGN.md); HBM fraction reported as the contract asks",
-                         "ms_per_launch": kkt_ms / max(kkt_n, 1), "active_sequences_per_launch": float(act.sum()), "fp64_gflops": kkt_gflops},
-            "roofline_fp64": {"bound": "fp64 tensor core (DMMA m8n8k4)", "kernel": "chd_k_kkt", "achieved": kkt_gflops, "unit": "GFLOP/s",
-                              "peak": dmma_peak, "peak_dfma": dfma_peak, "frac": (kkt_gflops / dmma_peak) if dmma_peak else None,
-                              "peak_source": "chd_measure_fp64_peak, measured in this run (all SMs)",
-                              "note": "band LDL^T flop count Na*(w+nb+1)^2 per active sequence and factorisation; one CTA per sequence, so at "
-                                      "most active_sequences_per_launch of the 148 SMs work"},
+            # dominant kernel: the KKT factorisation runs on the fp64 tensor-core pipe (DMMA) and is bound by that pipe's latency
+            # chain, not by HBM; its peak is measured in this run because MEASURED_PEAKS.json carries no
+            # fp64 figure.  The HBM view of the same kernel (the north star asks for it) follows as `roofline_hbm`.
+            "roofline": {"bound": "tensor", "kernel": "chd_k_kkt", "pipe": "fp64 tensor core (DMMA m8n8k4)",
+                         "achieved": kkt_gflops / 1e3, "peak": (dmma_peak / 1e3) if dmma_peak else None, "unit": "TFLOP/s",
+                         "frac": (kkt_gflops / dmma_peak) if dmma_peak else None, "traffic": traffic,
+                         "peak_source": "chd_measure_fp64_peak: DMMA loop on all SMs, measured in this run (no fp64 entry in MEASURED_PEAKS.json)",
+                         "peak_dfma": (dfma_peak / 1e3) if dfma_peak else None,
+                         "algorithmic_flops": kkt_flops, "ms_per_launch": kkt_ms / max(kkt_n, 1),
+                         "active_sequences_per_launch": float(act.sum()),
+                         "note": "band LDL^T flop count Na*(w+nb+1)^2 per active sequence and factorisation; one CTA per sequence, so at "
+                                 "most active_sequences_per_launch of the 148 SMs work"},
+            "roofline_hbm": {"bound": "hbm", "kernel": "chd_k_kkt", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": launch_bytes, "peak_source": peak_src},
             "kernels": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()},
             "roofline_eval": {"bound": "hbm", "kernel": "chd_k_eval", "achieved": eval_ach, "peak": hbm_peak, "unit": "GB/s",
                               "frac": eval_ach / hbm_peak},
