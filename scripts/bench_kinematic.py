@@ -33,7 +33,7 @@ def main():
         out["kinopt_s_" + tag] = dt
         out["kinopt_cost_" + tag] = res[-1]["stage2"]["cost"]
     # IK of apply_results on a 69-joint skeleton
-    from tests_golden_shim import ybot_like
+    from bench_skeletons import ybot_like
     names, parents, off = ybot_like()
     rng = np.random.default_rng(0)
     J = len(names)
