@@ -7,7 +7,7 @@ import pytest
 from hypothesis import given, settings, strategies as st
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 10_000), n_ee=st.sampled_from([2, 4]), N=st.integers(3, 40))
 def test_solution_file_round_trip_through_load_results(chd, tmp_path_factory, seed, n_ee, N):
     """write_solution (phys_optim.cpp:63-143 layout, 10 significant digits) -> load_towr_results: positions come back with
@@ -31,7 +31,7 @@ def test_solution_file_round_trip_through_load_results(chd, tmp_path_factory, se
     np.testing.assert_allclose(chd.results.rot_zyx(r.base_rot), r.base_R, atol=1e-9)      # base_rot are the Euler angles of base_R
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 10_000), F=st.integers(1, 6))
 def test_bvh_save_load_round_trip(chd, tmp_path_factory, seed, F):
     """save_bvh (Z Y X channels carrying the Euler angles of Rz Ry Rx) -> load_bvh -> local_transforms: same skeleton, same
@@ -53,7 +53,7 @@ def test_bvh_save_load_round_trip(chd, tmp_path_factory, seed, F):
     np.testing.assert_allclose(chd.prepare.euler_zyx_from_matrix(a.rotations), e, atol=1e-9)
 
 
-@settings(max_examples=15, deadline=None)
+@settings(max_examples=15, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 10_000), F=st.integers(1, 7), n=st.integers(1, 5))
 def test_block_pentadiagonal_solver(chd, seed, F, n):
     import torch
@@ -76,7 +76,7 @@ def test_block_pentadiagonal_solver(chd, seed, F, n):
         np.testing.assert_allclose(s.numpy(), ref.numpy(), rtol=1e-9, atol=1e-11)
 
 
-@settings(max_examples=15, deadline=None)
+@settings(max_examples=15, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 10_000), eps=st.sampled_from([1.35, 1.5, 2.2]))
 def test_huber_fit_first_order_conditions(chd, seed, eps):
     """At the returned point the gradient of the concomitant-scale Huber objective vanishes (to the L-BFGS tolerance) and
@@ -97,7 +97,7 @@ def test_huber_fit_first_order_conditions(chd, seed, eps):
     assert np.abs(gw).max() < 1e-3 * scale and abs(gc) < 1e-3 * scale / 25.0 and abs(gs) < 1e-2
 
 
-@settings(max_examples=10, deadline=None)
+@settings(max_examples=10, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 1000))
 def test_ik_reaches_reachable_targets(chd, seed):
     """Targets generated by the skeleton itself are reachable: the damped IK drives the error to (near) zero from a perturbed pose."""
