@@ -161,7 +161,7 @@ def test_switch_time_columns_finite_differences(chd):
 def test_switch_time_columns_finite_differences_random_points(chd):
     from hypothesis import given, settings, strategies as st
 
-    @settings(max_examples=4, deadline=None)
+    @settings(max_examples=4, deadline=None, derandomize=True)
     @given(st.integers(min_value=0, max_value=10_000))
     def run(seed):
         _fd_check(chd, chd.synth.make_problem(seed % 7, n_frames=40, n_ee=2 if seed % 2 else 4), seed)
