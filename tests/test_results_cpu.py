@@ -121,3 +121,23 @@ def test_retarget_matches_reference(chd):
     np.testing.assert_allclose(a.positions, g["pos"], atol=2e-6)
     np.testing.assert_allclose(a.global_positions(), g["gpos"], atol=2e-5)
     np.testing.assert_allclose(a.positions[:, 1:], np.tile(a.offsets[None, 1:], (a.positions.shape[0], 1, 1)), atol=0)   # bones restored
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_reader_parses_files_written_by_the_reference(chd, case):
+    """Row A1 on the reference's own output: the four files its `prepare_input` wrote (Python `str(float)` tokens) go through
+    `read_phys_inputs` -- the reader that mirrors phys_optim.cpp:155-267 -- and give the problem our own prepare step builds."""
+    s0, s1, comb, fps = CASES[case]
+    d = os.path.join(G, case)
+    q = chd.io_formats.read_phys_inputs(os.path.join(d, "phys_in"), s1 - s0)
+    b = chd.prepare.load_bvh(d + "/anim.bvh")
+    n, pt = [[float(v) for v in l.split()] for l in open(d + "/floor.txt").read().splitlines()[:2]]
+    p = chd.prepare.build_problem(b, n, pt, np.load(d + "/foot_contacts.npy"), chd.prepare.CHARACTERS[case.split("_")[0]](), s0, s1, 1.0 / fps, comb)
+    assert q.n_frames == p.n_frames == s1 - s0 and q.n_ee == 4
+    for k in ("hip_left", "hip_right", "inertia", "base_lin", "base_ang", "ee_pos", "floor_normal", "floor_point"):
+        np.testing.assert_allclose(getattr(q, k), getattr(p, k), rtol=0, atol=2e-9, err_msg=k)
+    for k in ("max_leg_length", "max_heel_length", "heel_dist", "body_mass", "dt"):
+        assert abs(getattr(q, k) - getattr(p, k)) < 2e-9, k
+    assert list(q.ee_start_contact) == list(p.ee_start_contact)
+    for e in range(4):
+        np.testing.assert_allclose(q.ee_durations[e], p.ee_durations[e], atol=1e-12)
