@@ -188,3 +188,40 @@ def solve_sharded(problems, weights=(0.4, 1.7, 0.3, 0.1, 0.1), device: int = 0, 
         return s.solve()
     finally:
         s.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Contact classifier: videos are independent too: shard by frame count, one gather of the int64 labels.
+# ---------------------------------------------------------------------------------------------------------------------
+def detect_contacts_sharded(raw, state_dict=None, device: int = 0, rank: int = 0, world: int = 1, group=None, detect_fn=None,
+                            gather_device=None):
+    """`raw`: list of (F_i, 25, 3) OpenPose keypoint arrays, identical on every rank.  Every rank runs
+    `ContactNet.detect` (`chd_contact_detect`: preprocessing, windows, network, votes on its GPU) on its shard, the
+    (slots, F_max, 4) int64 label blocks are gathered once and put back in input order.  Returns the list of (F_i, 4) labels.
+    `detect_fn(list_of_raw) -> list of (F_i, 4)` replaces the CUDA path in the CPU tests."""
+    import torch
+    n = len(raw)
+    shards = shard_by_work([float(r.shape[0]) for r in raw], world)
+    slots = pad_to(shards)
+    f_max = max(int(r.shape[0]) for r in raw)
+    mine = shards[rank]
+    # The reference pads every video of a batch to the batch's longest one by repeating the last frame
+    # (real_video_dataset.py:165-191) and votes over the padded windows before trimming, so the last labels of a video
+    # depend on the longest video it is batched with.  To return exactly what one unsharded call returns, a shard that does
+    # not hold the globally longest video carries it along (its labels are dropped).
+    longest = max(range(n), key=lambda i: (raw[i].shape[0], -i))
+    batch = [raw[i] for i in mine] + ([raw[longest]] if mine and longest not in mine else [])
+    if detect_fn is None:
+        from .contact import ContactNet
+        net = ContactNet(state_dict, device=device)
+        labels = net.detect(batch)[0][:len(mine)] if mine else []
+        net.close()
+    else:
+        labels = detect_fn(batch)[:len(mine)] if mine else []
+    dev = gather_device if gather_device is not None else (torch.device("cuda", device) if detect_fn is None else torch.device("cpu"))
+    block = torch.zeros((slots, f_max, 4), dtype=torch.int64, device=dev)
+    for k, lab in enumerate(labels):
+        block[k, :lab.shape[0]] = torch.as_tensor(np.asarray(lab, dtype=np.int64), device=dev)
+    gathered = gather_samples(block, world, group).cpu().numpy()
+    full = unshard(gathered, shards, slots)
+    return [full[i, :raw[i].shape[0]] for i in range(n)]

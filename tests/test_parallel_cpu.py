@@ -103,3 +103,46 @@ def test_solve_sharded_gloo(tmp_path, chd):
     np.testing.assert_array_equal(r0["stage_status"], ref["stage_status"])
     np.testing.assert_array_equal(r0["stage_iters"], ref["stage_iters"])
     assert (r0["success"] == 1).all()
+
+
+def _oracle_detect_fn(sd):
+    def fn(raws):
+        from oracle import contact as oc
+        frames, lens = oc.preprocess_videos(raws)
+        logits = oc.forward_torch(sd, oc.windows_from_frames(frames))
+        return [oc.vote(logits[i], int(lens[i])) for i in range(len(raws))]
+    return fn
+
+
+def _worker_contacts(rank, world, port, tmp):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import torch.distributed as dist
+    import chd
+    from make_contact_golden import contact_weights, synth_keypoints
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    raw = [synth_keypoints(40 + i, 30 + 7 * i) for i in range(5)]                  # ragged lengths, odd count
+    out = chd.parallel.detect_contacts_sharded(raw, rank=rank, world=world, detect_fn=_oracle_detect_fn(contact_weights(0)))
+    np.savez(os.path.join(tmp, "c%d.npz" % rank), *out)
+    dist.destroy_process_group()
+
+
+def test_detect_contacts_sharded_gloo(tmp_path, chd):
+    """Contact path across ranks: videos sharded by length, one gather of the int64 labels, input order restored."""
+    import sys
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_contact_golden import contact_weights, synth_keypoints
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker_contacts, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(str(tmp_path / "c0.npz")), np.load(str(tmp_path / "c1.npz"))
+    raw = [synth_keypoints(40 + i, 30 + 7 * i) for i in range(5)]
+    ref = _oracle_detect_fn(contact_weights(0))(raw)
+    for i in range(5):
+        a, b = r0["arr_%d" % i], r1["arr_%d" % i]
+        assert a.dtype == np.int64 and a.shape == (30 + 7 * i, 4)
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, ref[i])
