@@ -217,6 +217,8 @@ def apply_results(res: TowrResults, anim_bvh: str, start_idx, end_idx, info: Cha
     upper-body joint's offset from the COM) and base orientation; with `run_ik` the upper-body joints, toes and (4-foot
     results) heels are IK targets."""
     b = load_bvh(anim_bvh)
+    start_idx = 0 if start_idx is None else start_idx
+    end_idx = b.n_frames if end_idx is None else end_idx
     anim = anim_from_bvh(b, start_idx, end_idx)
     n_feet = res.feet_pos.shape[1]
     if info.heel_inds is None and n_feet == 4:
